@@ -1,0 +1,370 @@
+// cpk_device.cuh -- device-side data structures, the "team" abstraction
+// (whole cooperative grid, or one CTA) and the memory-model primitives used by
+// the persistent solver kernels.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpk {
+
+constexpr int kBlock      = 1024;   // threads per CTA: 1 CTA per SM, <=64 regs/thread
+constexpr int kWarpsPerCta = kBlock / 32;
+constexpr int kRedMax     = 8;      // values reduced together in one team reduction
+constexpr unsigned FULL   = 0xffffffffu;
+
+// phase slots of DevStatus::phase_cycles (mirror CPK_PH_* of cpk_b200.h)
+constexpr int CPK_PH_SPMV_ = 0, CPK_PH_LDL_ = 1, CPK_PH_RESID_ = 2, CPK_PH_VEC_ = 3, CPK_PH_OTHER_ = 4;
+// device-side copies of cpk_status codes
+constexpr int CPK_ERR_INDEFINITE_ = -5, CPK_ERR_BREAKDOWN_ = -6, CPK_ERR_TIMEOUT_ = -7;
+
+// ---------------------------------------------------------------------------
+// matrices
+// ---------------------------------------------------------------------------
+// SELL-32 (sliced ELLPACK, slice height = warp) with a per-lane row map, plus a
+// CSR remainder for rows too long to pad ("warp per row").  Immutable for the
+// lifetime of a kernel, so loads go through the non-coherent path.
+struct DevSell {
+    int nrows, ncols;
+    int nslices;
+    const int    *sptr;     // [nslices+1] element offset of each slice (multiple of 32)
+    const int    *col;      // padded entries: val = 0, col = a valid column of that row (or 0)
+    const double *val;
+    const int    *rowmap;   // [nslices*32] output row of each lane, -1 = no row
+    int nlong;              // rows handled warp-per-row
+    const int    *lrow;     // [nlong] row index
+    const int    *lptr;     // [nlong+1]
+    const int    *lcol;
+    const double *lval;
+};
+
+// One triangular sweep of the LDL' solve in "item" form: an item is a SELL
+// slice of <=32 rows of the same dependency level, processed by one warp.
+// Column indices address the dependency buffer directly (LDL row ids).
+struct DevSweep {
+    int nitems;
+    const int    *sptr;     // [nitems+1]
+    const int    *col;      // -1 = padding
+    const double *val;
+    const int    *rid;      // [nitems*32] LDL row id, -1 = idle lane
+    const int    *pidx;     // [nitems*32] index into the user vector (perm[rid])
+};
+
+struct DevLdl {
+    int N, nA, nC;
+    DevSweep fwd, bwd;
+    // D-solve data, indexed like bwd.rid (per lane of the backward sweep)
+    const double *b_d;      // own diagonal entry
+    const int    *b_partner;// LDL row id of the 2x2 partner or -1
+    const double *b_e;      // off-diagonal of the 2x2 block (valid if partner>=0)
+    const double *b_dp;     // partner's diagonal entry
+    // sync-free state (row-id indexed)
+    double *wbuf, *ybuf;
+    int    *wflag, *yflag;
+    int    *epoch;          // [1] device-resident solve counter
+    // K_P = [A B'; B C] for the refinement residual and `divide`
+    DevSell KP;
+    DevSell K12, K22;       // B' (nA x nC) and C (nC x nC) for the stateful residual update
+    double *atycy;          // [N] = [Aty; Cy]
+    double *rvec;           // [N] refinement residual
+    // options (opLDL2.m:45-50)
+    int    nitref;
+    double itref_tol;
+    int    force_itref;
+    int    residual_update;
+    int    ru_stateful;
+    int    track_rnorm;
+    double *rnorm_out;      // [1] op.rNorm
+};
+
+struct DevStatus {
+    long long niters;
+    int   solved;
+    int   status;
+    int   err;              // cpk_status (0 ok)
+    int   err_iter;
+    int   err_second;
+    int   shifted;
+    double err_value;
+    long long hist_len;
+    long long napply, nldlsolve, nresid;
+    unsigned long long phase_cycles[8];
+};
+
+struct DevSystem {
+    int n, m, N;
+    DevSell HC;             // blkdiag(H, C), N x N
+    DevSell Hn;             // H alone (n x n) and
+    DevSell Cm;             // C alone (m x m): stand-alone matvec
+    DevLdl  M;
+};
+
+struct SolveArgs {
+    int     solver;
+    int     reg_mode;       // 1: rhs shift / un-shift of reg_cpkrylov.m:153-173
+    const double *b;        // n (solve) or N (reg) entries
+    double *x;              // N entries out: [x; y]
+    double  atol, rtol, btol;
+    long long itmax;
+    int     restart, mem;
+    int     profile;
+    double *work;           // workspace
+    long long work_len;     // doubles
+    double *hist;           // 3 rows
+    long long hist_cap;
+    double *gs;             // GMRES/DQGMRES scalar scratch in global memory
+    DevStatus *status;
+};
+
+// ---------------------------------------------------------------------------
+// memory-model primitives
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// L2-coherent data accesses for buffers produced by other SMs inside a phase
+__device__ __forceinline__ double ld_cg(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg(double *p, double v) {
+    asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile(const int *p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Team-shared control block in global memory (one per launch team).
+struct TeamCtl {
+    unsigned bar;           // monotonically increasing arrival counter
+    int      abort;         // set by the watchdog; every wait loop polls it
+    unsigned pad[30];
+};
+
+constexpr long long kWatchdogCycles = 4000000000LL;   // ~2 s of SM clocks
+
+// ---------------------------------------------------------------------------
+// Team = the set of threads that cooperates on ONE system.
+//   GridTeam: all CTAs of a cooperative launch (large systems)
+//   CtaTeam : a single CTA (small systems; a batch launch runs many of them)
+// Both expose: tid/nthreads, gwarp/nwarps/lane, sync(), reduce<K>().
+// ---------------------------------------------------------------------------
+struct TeamShared {
+    double red[kWarpsPerCta][kRedMax];
+    double out[kRedMax];
+};
+
+struct GridTeam {
+    int tid, nthreads, gwarp, nwarps, lane;
+    TeamCtl *ctl;
+    double  *partials;      // [2][kRedMax][gridDim.x]
+    TeamShared *sh;
+    unsigned bar_target;
+    unsigned red_parity;
+
+    __device__ void init(TeamCtl *c, double *p, TeamShared *s) {
+        tid = blockIdx.x * blockDim.x + threadIdx.x;
+        nthreads = gridDim.x * blockDim.x;
+        gwarp = tid >> 5;
+        nwarps = nthreads >> 5;
+        lane = threadIdx.x & 31;
+        ctl = c; partials = p; sh = s;
+        bar_target = 0; red_parity = 0;
+        wide = nullptr; wide_cols = 0; wide_parity = 0;
+    }
+    __device__ __forceinline__ bool aborted() const { return ld_volatile(&ctl->abort) != 0; }
+    __device__ __forceinline__ void set_abort() const { atomicExch(&ctl->abort, 1); }
+    __device__ __forceinline__ bool leader() const { return tid == 0; }
+    __device__ __forceinline__ bool cta_leader() const { return threadIdx.x == 0; }
+    __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+
+    __device__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bar_target += gridDim.x;
+            red_release_add(&ctl->bar, 1u);
+            unsigned spins = 0;
+            long long t0 = clock64();
+            while ((int)(ld_acquire(&ctl->bar) - bar_target) < 0) {
+                if ((++spins & 0xff) == 0) {
+                    if (aborted()) break;
+                    if (clock64() - t0 > kWatchdogCycles) { set_abort(); break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // All-reduce (sum) of K per-thread values; every thread of the team gets the
+    // same bits: fixed butterfly inside the warp, fixed warp order in the CTA,
+    // fixed CTA order across the grid.  Contains one grid barrier.
+    template <int K>
+    __device__ void reduce(double (&v)[K]) {
+        static_assert(K <= kRedMax, "reduce width");
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+        const int w = threadIdx.x >> 5;
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh->red[w][k] = v[k];
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double s = sh->red[lane][k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                if (lane == 0)
+                    st_cg(&partials[((size_t)red_parity * kRedMax + k) * gridDim.x + blockIdx.x], s);
+            }
+        }
+        sync();
+        if (w < K) {
+            const double *p = &partials[((size_t)red_parity * kRedMax + w) * gridDim.x];
+            double s = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += ld_cg(&p[b]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) sh->out[w] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = sh->out[k];
+        __syncthreads();            // sh->out / sh->red are free again
+        red_parity ^= 1u;
+    }
+
+    // Multi-column reductions (Arnoldi coefficients): block-reduce K values and
+    // park them as columns col0..col0+K-1 of a wide partial array [cols][grid];
+    // after ONE team barrier wide_collect() finishes all columns at once.
+    double  *wide;          // [2][wide_cols][gridDim.x]
+    int      wide_cols;
+    unsigned wide_parity;
+    template <int K>
+    __device__ void wide_store(double (&v)[K], int col0, int nvalid, double * /*dst*/) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+        const int w = threadIdx.x >> 5;
+        __syncthreads();            // sh->red free (previous chunk consumed)
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh->red[w][k] = v[k];
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double s = sh->red[lane][k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                if (lane == 0 && k < nvalid)
+                    st_cg(&wide[((size_t)wide_parity * wide_cols + col0 + k) * gridDim.x + blockIdx.x], s);
+            }
+        }
+    }
+    __device__ void wide_collect(int ncols, double *dst /*shared*/) {
+        sync();
+        const int w = threadIdx.x >> 5;
+        for (int c = w; c < ncols; c += kWarpsPerCta) {
+            const double *p = &wide[((size_t)wide_parity * wide_cols + c) * gridDim.x];
+            double s = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += ld_cg(&p[b]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) dst[c] = s;
+        }
+        __syncthreads();
+        wide_parity ^= 1u;
+    }
+};
+
+struct CtaTeam {
+    int tid, nthreads, gwarp, nwarps, lane;
+    TeamCtl *ctl;
+    TeamShared *sh;
+
+    __device__ void init(TeamCtl *c, double *, TeamShared *s) {
+        tid = threadIdx.x;
+        nthreads = blockDim.x;
+        gwarp = tid >> 5;
+        nwarps = nthreads >> 5;
+        lane = tid & 31;
+        ctl = c; sh = s;
+    }
+    __device__ __forceinline__ bool aborted() const { return ld_volatile(&ctl->abort) != 0; }
+    __device__ __forceinline__ void set_abort() const { atomicExch(&ctl->abort, 1); }
+    __device__ __forceinline__ bool leader() const { return tid == 0; }
+
+    // CTA barrier + make global writes of the CTA visible to its own later loads
+    // (L1 is per SM, the team never leaves it; __syncthreads orders them).
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ bool cta_leader() const { return threadIdx.x == 0; }
+    __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+
+    template <int K>
+    __device__ void wide_store(double (&v)[K], int col0, int nvalid, double *dst /*shared*/) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+        const int w = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh->red[w][k] = v[k];
+        __syncthreads();
+        if (w < K && w < nvalid) {
+            double s = (lane < nwarps) ? sh->red[lane][w] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) dst[col0 + w] = s;
+        }
+    }
+    __device__ void wide_collect(int, double *) { __syncthreads(); }
+
+    template <int K>
+    __device__ void reduce(double (&v)[K]) {
+        static_assert(K <= kRedMax, "reduce width");
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+        const int w = threadIdx.x >> 5;
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh->red[w][k] = v[k];
+        __syncthreads();
+        if (w < K) {
+            double s = (lane < nwarps) ? sh->red[lane][w] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) sh->out[w] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = sh->out[k];
+        __syncthreads();
+    }
+};
+
+#define TEAM_FOR(T, i, N) for (int i = (T).tid; i < (N); i += (T).nthreads)
+
+}  // namespace cpk

@@ -1,0 +1,1162 @@
+// cpk_host.cu -- host side of libcpk_b200.so: handle registry, one-time analysis
+// and upload of the operators (SELL-32 matrices, level-ordered LDL' sweeps),
+// kernel entry points and the C ABI of include/cpk_b200.h.
+//
+// Nothing here runs per Krylov iteration: a solve is ONE kernel launch.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cpk_b200.h"
+#include "cpk_solvers.cuh"
+
+using namespace cpk;
+
+// ===========================================================================
+// errors
+// ===========================================================================
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                    \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(CPK_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
+    } while (0)
+
+// ===========================================================================
+// host sparse helpers
+// ===========================================================================
+struct HCsr {
+    int nrows = 0, ncols = 0;
+    std::vector<int64_t> ptr;
+    std::vector<int> col;
+    std::vector<double> val;
+    int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
+    int len(int r) const { return (int)(ptr[r + 1] - ptr[r]); }
+};
+
+static bool csc_ok(const cpk_csc *A)
+{
+    return A && A->nrows >= 0 && A->ncols >= 0 && A->colptr && (A->colptr[A->ncols] == 0 || (A->rowind && A->val));
+}
+
+// CSR of A (rows of A), from MATLAB CSC: a counting-sort transpose; column
+// indices inside a row come out ascending.
+static HCsr csr_from_csc(const cpk_csc &A)
+{
+    HCsr R;
+    R.nrows = (int)A.nrows; R.ncols = (int)A.ncols;
+    const int64_t nnz = A.colptr[A.ncols];
+    R.ptr.assign((size_t)R.nrows + 1, 0);
+    for (int64_t k = 0; k < nnz; ++k) R.ptr[A.rowind[k] + 1]++;
+    for (int i = 0; i < R.nrows; ++i) R.ptr[i + 1] += R.ptr[i];
+    R.col.resize(nnz); R.val.resize(nnz);
+    std::vector<int64_t> next(R.ptr.begin(), R.ptr.end() - 1);
+    for (int64_t j = 0; j < A.ncols; ++j)
+        for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; ++k) {
+            const int64_t p = next[A.rowind[k]]++;
+            R.col[p] = (int)j; R.val[p] = A.val[k];
+        }
+    return R;
+}
+// CSR of A' : the CSC arrays read as rows (sorted by index inside each row).
+static HCsr csr_of_transpose(const cpk_csc &A)
+{
+    HCsr R;
+    R.nrows = (int)A.ncols; R.ncols = (int)A.nrows;
+    const int64_t nnz = A.colptr[A.ncols];
+    R.ptr.assign(A.colptr, A.colptr + A.ncols + 1);
+    R.col.resize(nnz); R.val.resize(nnz);
+    for (int j = 0; j < R.nrows; ++j) {
+        const int64_t b = R.ptr[j], e = R.ptr[j + 1];
+        std::vector<std::pair<int, double>> tmp;
+        bool sorted = true;
+        for (int64_t k = b; k < e; ++k) {
+            if (k > b && A.rowind[k] < A.rowind[k - 1]) sorted = false;
+            R.col[k] = (int)A.rowind[k]; R.val[k] = A.val[k];
+        }
+        if (!sorted) {
+            tmp.reserve(e - b);
+            for (int64_t k = b; k < e; ++k) tmp.emplace_back(R.col[k], R.val[k]);
+            std::sort(tmp.begin(), tmp.end(), [](auto &x, auto &y) { return x.first < y.first; });
+            for (int64_t k = b; k < e; ++k) { R.col[k] = tmp[k - b].first; R.val[k] = tmp[k - b].second; }
+        }
+    }
+    return R;
+}
+
+// [A 0; 0 C] or general 2x2 block assembly by rows.  Blocks may be null (zero).
+static HCsr block2x2(const HCsr *A11, const HCsr *A12, const HCsr *A21, const HCsr *A22, int n1, int n2)
+{
+    HCsr R;
+    R.nrows = n1 + n2; R.ncols = n1 + n2;
+    R.ptr.assign((size_t)R.nrows + 1, 0);
+    auto rowlen = [](const HCsr *M, int r) { return M ? M->len(r) : 0; };
+    for (int i = 0; i < n1; ++i) R.ptr[i + 1] = R.ptr[i] + rowlen(A11, i) + rowlen(A12, i);
+    for (int i = 0; i < n2; ++i) R.ptr[n1 + i + 1] = R.ptr[n1 + i] + rowlen(A21, i) + rowlen(A22, i);
+    R.col.resize(R.ptr.back()); R.val.resize(R.ptr.back());
+    auto put = [&](const HCsr *M, int r, int off, int64_t &p) {
+        if (!M) return;
+        for (int64_t k = M->ptr[r]; k < M->ptr[r + 1]; ++k) { R.col[p] = M->col[k] + off; R.val[p] = M->val[k]; ++p; }
+    };
+    for (int i = 0; i < n1; ++i) { int64_t p = R.ptr[i]; put(A11, i, 0, p); put(A12, i, n1, p); }
+    for (int i = 0; i < n2; ++i) { int64_t p = R.ptr[n1 + i]; put(A21, i, 0, p); put(A22, i, n1, p); }
+    return R;
+}
+
+// ---------------------------------------------------------------------------
+// SELL-32-sigma builder.  Rows are stably sorted by length inside windows of
+// `sigma` rows (keeps x-locality, removes padding), cut into slices of 32.
+// Rows much longer than the mean go to the CSR "long" list (warp per row).
+// ---------------------------------------------------------------------------
+struct HSell {
+    int nrows = 0, ncols = 0, nslices = 0;
+    std::vector<int> sptr, col, rowmap;
+    std::vector<double> val;
+    std::vector<int> lrow, lptr, lcol;
+    std::vector<double> lval;
+    int64_t nnz = 0;
+};
+
+static int sell_sigma()
+{
+    static int s = [] { const char *e = getenv("CPK_SELL_SIGMA"); int v = e ? atoi(e) : 4096; return std::max(32, v / 32 * 32); }();
+    return s;
+}
+
+// Appends the rows [r0, r1) of A (column offset coff, row offset roff) as new slices.
+static void sell_append(HSell &S, const HCsr &A, int r0, int r1, int coff, int roff)
+{
+    const int64_t nnz = A.ptr[r1] - A.ptr[r0];
+    const double mean = (r1 > r0) ? (double)nnz / (r1 - r0) : 0.0;
+    const int long_thr = (int)std::max(128.0, 8.0 * mean);
+    std::vector<int> rows;
+    rows.reserve(r1 - r0);
+    for (int r = r0; r < r1; ++r) {
+        if (A.len(r) > long_thr) {
+            if (S.lptr.empty()) S.lptr.push_back(0);
+            S.lrow.push_back(r + roff);
+            for (int64_t k = A.ptr[r]; k < A.ptr[r + 1]; ++k) { S.lcol.push_back(A.col[k] + coff); S.lval.push_back(A.val[k]); }
+            S.lptr.push_back((int)S.lcol.size());
+        } else rows.push_back(r);
+    }
+    const int sigma = sell_sigma();
+    if (S.sptr.empty()) S.sptr.push_back(0);
+    for (size_t w0 = 0; w0 < rows.size(); w0 += sigma) {
+        const size_t w1 = std::min(rows.size(), w0 + (size_t)sigma);
+        std::stable_sort(rows.begin() + w0, rows.begin() + w1, [&](int a, int b) { return A.len(a) > A.len(b); });
+        for (size_t s0 = w0; s0 < w1; s0 += 32) {
+            const size_t s1 = std::min(w1, s0 + 32);
+            int width = 0;
+            for (size_t t = s0; t < s1; ++t) width = std::max(width, A.len(rows[t]));
+            const size_t base = S.col.size();
+            S.col.resize(base + (size_t)width * 32, 0);
+            S.val.resize(base + (size_t)width * 32, 0.0);
+            for (int lane = 0; lane < 32; ++lane) {
+                const size_t t = s0 + lane;
+                if (t < s1) {
+                    const int r = rows[t];
+                    S.rowmap.push_back(r + roff);
+                    const int len = A.len(r);
+                    int lastc = 0;
+                    for (int j = 0; j < width; ++j) {
+                        if (j < len) {
+                            lastc = A.col[A.ptr[r] + j] + coff;
+                            S.col[base + (size_t)j * 32 + lane] = lastc;
+                            S.val[base + (size_t)j * 32 + lane] = A.val[A.ptr[r] + j];
+                        } else S.col[base + (size_t)j * 32 + lane] = lastc;
+                    }
+                } else S.rowmap.push_back(-1);
+            }
+            S.sptr.push_back((int)S.col.size());
+            S.nslices++;
+        }
+    }
+    S.nnz += nnz;
+}
+
+static HSell build_sell(const HCsr &A)
+{
+    HSell S;
+    S.nrows = A.nrows; S.ncols = A.ncols;
+    sell_append(S, A, 0, A.nrows, 0, 0);
+    if (S.sptr.empty()) S.sptr.push_back(0);
+    if (S.lptr.empty()) S.lptr.push_back(0);
+    return S;
+}
+
+// ---------------------------------------------------------------------------
+// Triangular sweep builder: rows grouped by dependency level, sorted by length
+// inside a level, cut into slices (items) that never straddle a level.
+// deps: CSR of the STRICT triangle in LDL index space.
+// ---------------------------------------------------------------------------
+struct HSweep {
+    int nitems = 0, nlevels = 0;
+    std::vector<int> sptr, col, rid, pidx;
+    std::vector<double> val;
+};
+
+static HSweep build_sweep(const HCsr &deps, const std::vector<int> &level, int nlevels, const std::vector<int64_t> &perm)
+{
+    HSweep W;
+    W.nlevels = nlevels;
+    const int N = deps.nrows;
+    std::vector<int> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (level[a] != level[b]) return level[a] < level[b];
+        return deps.len(a) > deps.len(b);
+    });
+    W.sptr.push_back(0);
+    size_t i0 = 0;
+    while (i0 < (size_t)N) {
+        size_t i1 = i0;
+        const int lev = level[order[i0]];
+        while (i1 < (size_t)N && i1 - i0 < 32 && level[order[i1]] == lev) ++i1;
+        int width = 0;
+        for (size_t t = i0; t < i1; ++t) width = std::max(width, deps.len(order[t]));
+        const size_t base = W.col.size();
+        W.col.resize(base + (size_t)width * 32, -1);
+        W.val.resize(base + (size_t)width * 32, 0.0);
+        for (int lane = 0; lane < 32; ++lane) {
+            const size_t t = i0 + lane;
+            if (t < i1) {
+                const int r = order[t];
+                W.rid.push_back(r);
+                W.pidx.push_back((int)perm[r]);
+                for (int j = 0; j < deps.len(r); ++j) {
+                    W.col[base + (size_t)j * 32 + lane] = deps.col[deps.ptr[r] + j];
+                    W.val[base + (size_t)j * 32 + lane] = deps.val[deps.ptr[r] + j];
+                }
+            } else { W.rid.push_back(-1); W.pidx.push_back(0); }
+        }
+        W.sptr.push_back((int)W.col.size());
+        W.nitems++;
+        i0 = i1;
+    }
+    return W;
+}
+
+// ===========================================================================
+// device objects
+// ===========================================================================
+struct DevArena {
+    std::vector<void *> ptrs;
+    int device = 0;
+    ~DevArena() { release(); }
+    void release() {
+        if (ptrs.empty()) return;
+        cudaSetDevice(device);
+        for (void *p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+    template <class T>
+    cudaError_t alloc(T **out, size_t count, bool zero = false) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        if (zero) { e = cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)); if (e != cudaSuccess) return e; }
+        *out = (T *)p;
+        return cudaSuccess;
+    }
+    template <class T>
+    cudaError_t upload(const T **out, const std::vector<T> &v) {
+        T *p = nullptr;
+        cudaError_t e = alloc(&p, v.size());
+        if (e != cudaSuccess) return e;
+        if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        *out = p;
+        return e;
+    }
+};
+
+static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d)
+{
+    cudaError_t e;
+    d.nrows = h.nrows; d.ncols = h.ncols; d.nslices = h.nslices;
+    if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.rowmap, h.rowmap)) != cudaSuccess) return e;
+    d.nlong = (int)h.lrow.size();
+    if ((e = ar.upload(&d.lrow, h.lrow)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.lptr, h.lptr)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.lcol, h.lcol)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.lval, h.lval)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+static cudaError_t upload_sweep(DevArena &ar, const HSweep &h, DevSweep &d)
+{
+    cudaError_t e;
+    d.nitems = h.nitems;
+    if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.rid, h.rid)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.pidx, h.pidx)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+enum ObjKind { OBJ_LDL2 = 1, OBJ_SYSTEM = 2 };
+
+struct Object {
+    ObjKind kind;
+    int device = 0;
+    virtual ~Object() {}
+};
+
+// per-device launch context: stream, events, team control block, partials
+struct DeviceCtx {
+    int device = -1;
+    int num_sms = 0;
+    int grid_blocks = 0;            // co-resident CTAs of the solver kernel
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    TeamCtl *ctl = nullptr;         // [kMaxBatch]
+    double *partials = nullptr;     // [2][kRedMax][grid]
+    double *wide = nullptr;         // [2][wide_cols][grid]
+    int wide_cols = 0;
+    DevStatus *h_status = nullptr;  // pinned
+    int h_status_cap = 0;
+};
+constexpr int kMaxBatch = 4096;
+static std::mutex g_mu;
+static std::unordered_map<int, std::unique_ptr<DeviceCtx>> g_dev;
+static std::unordered_map<uint64_t, std::unique_ptr<Object>> g_obj;
+static uint64_t g_next = 1;
+
+struct Ldl2 : Object {
+    DevArena ar;
+    DevLdl d{};
+    int64_t nnz_off = 0, lev_f = 0, lev_b = 0, n2x2 = 0;
+    DevSystem *d_sys_alone = nullptr;   // DevSystem with only M filled (stand-alone apply)
+    double *d_z = nullptr, *d_y = nullptr;
+    DevStatus *d_status = nullptr;
+    bool in_system = false;
+    Ldl2() { kind = OBJ_LDL2; }
+};
+
+struct System : Object {
+    DevArena ar;
+    Ldl2 *M = nullptr;
+    uint64_t M_handle = 0;
+    DevSystem h{};                  // host copy (device pointers inside)
+    DevSystem *d_sys = nullptr;
+    SolveArgs *d_args = nullptr;
+    DevStatus *d_status = nullptr;
+    double *d_b = nullptr, *d_x = nullptr;
+    // grow-only buffers
+    DevArena war;
+    double *d_work = nullptr; long long work_len = 0;
+    double *d_hist = nullptr; long long hist_cap = 0;
+    double *d_gs = nullptr; long long gs_len = 0;
+    System() { kind = OBJ_SYSTEM; }
+};
+
+// forward decls of kernels
+extern "C" {
+const void *cpk_kernel_cpcg(int grid);
+const void *cpk_kernel_cpcglanczos(int grid);
+const void *cpk_kernel_cpminres(int grid);
+const void *cpk_kernel_cpsymmlq(int grid);
+const void *cpk_kernel_cpgmres(int grid);
+const void *cpk_kernel_cpdqgmres(int grid);
+}
+static const void *solver_kernel(int solver, bool grid)
+{
+    switch (solver) {
+        case CPK_CPCG: return cpk_kernel_cpcg(grid);
+        case CPK_CPCGLANCZOS: return cpk_kernel_cpcglanczos(grid);
+        case CPK_CPMINRES: return cpk_kernel_cpminres(grid);
+        case CPK_CPSYMMLQ: return cpk_kernel_cpsymmlq(grid);
+        case CPK_CPGMRES: return cpk_kernel_cpgmres(grid);
+        case CPK_CPDQGMRES: return cpk_kernel_cpdqgmres(grid);
+    }
+    return nullptr;
+}
+template <bool GRID> __global__ void k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st,
+                                             TeamCtl *ctl, double *partials);
+template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y);
+
+static int get_device_ctx(int device, DeviceCtx **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_dev.find(device);
+    if (it != g_dev.end()) { *out = it->second.get(); return CPK_OK; }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        return fail(CPK_ERR_CUDA, "no CUDA device available (libcpk_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= cnt) return fail(CPK_ERR_ARG, "device %d out of range (%d visible)", device, cnt);
+    CUDA_TRY(cudaSetDevice(device));
+    auto c = std::make_unique<DeviceCtx>();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(CPK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    c->num_sms = prop.multiProcessorCount;
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return fail(CPK_ERR_CUDA, "device does not support cooperative launch");
+    // allow the largest dynamic shared memory the solver kernels may ask for
+    int per_sm = 1;
+    for (int sv = 0; sv < 6; ++sv)
+        for (int g = 0; g < 2; ++g) {
+            const void *k = solver_kernel(sv, g);
+            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
+            if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
+        }
+    c->grid_blocks = c->num_sms;    // one CTA per SM
+    if (const char *e = getenv("CPK_GRID_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= c->num_sms * per_sm) c->grid_blocks = v; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaMalloc(&c->ctl, sizeof(TeamCtl) * kMaxBatch));
+    CUDA_TRY(cudaMalloc(&c->partials, sizeof(double) * 2 * kRedMax * c->grid_blocks));
+    CUDA_TRY(cudaMallocHost(&c->h_status, sizeof(DevStatus) * kMaxBatch));
+    c->h_status_cap = kMaxBatch;
+    *out = c.get();
+    g_dev[device] = std::move(c);
+    return CPK_OK;
+}
+
+static int ensure_wide(DeviceCtx *dc, int cols)
+{
+    if (cols <= dc->wide_cols) return CPK_OK;
+    if (dc->wide) cudaFree(dc->wide);
+    dc->wide = nullptr; dc->wide_cols = 0;
+    CUDA_TRY(cudaMalloc(&dc->wide, sizeof(double) * 2 * (size_t)cols * dc->grid_blocks));
+    dc->wide_cols = cols;
+    return CPK_OK;
+}
+
+template <class T>
+static T *lookup(cpk_handle h, ObjKind kind)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_obj.find(h);
+    if (it == g_obj.end() || it->second->kind != kind) return nullptr;
+    return static_cast<T *>(it->second.get());
+}
+static cpk_handle register_obj(std::unique_ptr<Object> o)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    const cpk_handle h = g_next++;
+    g_obj[h] = std::move(o);
+    return h;
+}
+
+// team selection: a system this small is solved by ONE CTA (barriers become
+// __syncthreads); larger ones by the whole cooperative grid.
+static bool use_grid(int N)
+{
+    static int thr = [] { const char *e = getenv("CPK_CTA_MAX_N"); return e ? atoi(e) : 24576; }();
+    if (const char *e = getenv("CPK_TEAM")) {
+        if (!strcmp(e, "grid")) return true;
+        if (!strcmp(e, "cta")) return false;
+    }
+    return N > thr;
+}
+
+// ===========================================================================
+// kernels
+// ===========================================================================
+template <bool GRID>
+__global__ void __launch_bounds__(kBlock, 1)
+k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl *ctl, double *partials)
+{
+    __shared__ TeamShared sh;
+    PhaseClock pc; pc.start(false, nullptr);
+    const DevLdl &M = sys->M;
+    VecIn in{z, nullptr, M.nA, false};
+    int epoch = *M.epoch;
+    if (GRID) {
+        GridTeam T; T.init(ctl, partials, &sh);
+        ldl2_apply(T, M, in, y, epoch, st, pc);
+        T.sync();
+        if (T.leader()) { *M.epoch = epoch; if (T.aborted()) st->err = CPK_ERR_TIMEOUT_; }
+    } else {
+        CtaTeam T; T.init(ctl, nullptr, &sh);
+        ldl2_apply(T, M, in, y, epoch, st, pc);
+        T.sync();
+        if (T.leader()) { *M.epoch = epoch; if (T.aborted()) st->err = CPK_ERR_TIMEOUT_; }
+    }
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(kBlock, 1)
+k_matvec(DevSell A, const double *x, double *y)
+{
+    if (GRID) {
+        GridTeam T; T.init(nullptr, nullptr, nullptr);
+        spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
+    } else {
+        CtaTeam T; T.init(nullptr, nullptr, nullptr);
+        spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
+    }
+}
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+// (C linkage comes from the declarations in cpk_b200.h)
+
+int cpk_version(void) { return 100; }
+
+int cpk_device_count(void)
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cnt;
+}
+
+int cpk_last_error(char *buf, int64_t buflen)
+{
+    if (!buf || buflen <= 0) return CPK_ERR_ARG;
+    snprintf(buf, (size_t)buflen, "%s", g_err.c_str());
+    return CPK_OK;
+}
+
+int64_t cpk_launch_count(void) { return g_launches; }
+
+// ---------------------------------------------------------------------------
+int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
+                    const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
+{
+    if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create: null output handle");
+    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !csc_ok(L) || !csc_ok(D) || !perm)
+        return fail(CPK_ERR_ARG, "Invalid number of arguments.");                   // opLDL2.m:61-63
+    if (A->nrows != A->ncols || C->nrows != C->ncols)
+        return fail(CPK_ERR_DIM, "First and last arguments must be square.");       // opLDL2.m:68-70
+    if (B->ncols != A->nrows || B->nrows != C->nrows)
+        return fail(CPK_ERR_DIM, "Incompatible dimensions.");                       // opLDL2.m:73-75
+    const int64_t nA = A->nrows, nC = C->nrows, N64 = nA + nC;
+    if (N64 >= (int64_t)1 << 30) return fail(CPK_ERR_UNSUPPORTED, "N = %lld exceeds int32 indexing", (long long)N64);
+    if (L->nrows != N64 || L->ncols != N64 || D->nrows != N64 || D->ncols != N64)
+        return fail(CPK_ERR_DIM, "LDL factors must be %lld x %lld", (long long)N64, (long long)N64);
+    const int N = (int)N64;
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+
+    // ---- permutation
+    std::vector<int64_t> p(perm, perm + N);
+    {
+        std::vector<char> seen(N, 0);
+        for (int k = 0; k < N; ++k) {
+            if (p[k] < 0 || p[k] >= N || seen[p[k]]) return fail(CPK_ERR_ARG, "perm is not a permutation of 0..N-1");
+            seen[p[k]] = 1;
+        }
+    }
+    // ---- D: 1x1 / 2x2 blocks
+    std::vector<double> d(N, 0.0), e(N, 0.0);
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t k = D->colptr[j]; k < D->colptr[j + 1]; ++k) {
+            const int64_t i = D->rowind[k];
+            if (i == j) d[j] = D->val[k];
+            else if (i == j + 1) e[j] = D->val[k];
+            else if (i == j - 1) { /* symmetric twin */ }
+            else if (D->val[k] != 0.0) return fail(CPK_ERR_ARG, "D is not block diagonal with 1x1/2x2 blocks");
+        }
+    std::vector<int> partner(N, -1);
+    int64_t n2 = 0;
+    for (int i = 0; i + 1 < N; ++i)
+        if (e[i] != 0.0) {
+            if (partner[i] >= 0) return fail(CPK_ERR_ARG, "overlapping 2x2 pivots in D");
+            partner[i] = i + 1; partner[i + 1] = i; ++n2;
+        }
+    // ---- L: strict lower triangle, rows (forward deps) and columns (backward deps)
+    HCsr Lrows, Lcols;
+    {
+        // strip diagonal / reject upper entries
+        std::vector<int64_t> cp(N + 1, 0), ri; std::vector<double> vv;
+        const int64_t nnzL = L->colptr[N];
+        ri.reserve(nnzL); vv.reserve(nnzL);
+        for (int64_t j = 0; j < N; ++j) {
+            for (int64_t k = L->colptr[j]; k < L->colptr[j + 1]; ++k) {
+                const int64_t i = L->rowind[k];
+                if (i < j) { if (L->val[k] != 0.0) return fail(CPK_ERR_ARG, "L is not lower triangular"); continue; }
+                if (i == j) continue;       // unit diagonal
+                ri.push_back(i); vv.push_back(L->val[k]);
+            }
+            cp[j + 1] = (int64_t)ri.size();
+        }
+        cpk_csc Ls{N, N, cp.data(), ri.data(), vv.data()};
+        Lrows = csr_from_csc(Ls);
+        Lcols = csr_of_transpose(Ls);
+    }
+    // ---- dependency levels
+    std::vector<int> lf(N, 0), lb(N, 0);
+    int nlf = 0, nlb = 0;
+    for (int i = 0; i < N; ++i) {
+        int lv = 0;
+        for (int64_t k = Lrows.ptr[i]; k < Lrows.ptr[i + 1]; ++k) lv = std::max(lv, lf[Lrows.col[k]] + 1);
+        lf[i] = lv; nlf = std::max(nlf, lv + 1);
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        int lv = 0;
+        for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) lv = std::max(lv, lb[Lcols.col[k]] + 1);
+        lb[i] = lv; nlb = std::max(nlb, lv + 1);
+    }
+    HSweep Wf = build_sweep(Lrows, lf, nlf, p);
+    HSweep Wb = build_sweep(Lcols, lb, nlb, p);
+    if ((int64_t)Wf.col.size() >= INT32_MAX || (int64_t)Wb.col.size() >= INT32_MAX)
+        return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
+    // D data per backward lane
+    std::vector<double> bd(Wb.rid.size(), 1.0), be(Wb.rid.size(), 0.0), bdp(Wb.rid.size(), 1.0);
+    std::vector<int> bpart(Wb.rid.size(), -1);
+    for (size_t s = 0; s < Wb.rid.size(); ++s) {
+        const int r = Wb.rid[s];
+        if (r < 0) continue;
+        bd[s] = d[r];
+        if (partner[r] >= 0) {
+            bpart[s] = partner[r];
+            be[s] = e[std::min(r, partner[r])];
+            bdp[s] = d[partner[r]];
+        }
+    }
+    // ---- K_P = [A B'; B C] by rows
+    HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
+    HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, (int)nA, (int)nC);
+    HSell sKP = build_sell(KP), sK12 = build_sell(Bt), sK22 = build_sell(Cr);
+    if ((int64_t)sKP.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
+
+    // ---- upload
+    auto o = std::make_unique<Ldl2>();
+    o->device = device; o->ar.device = device;
+    CUDA_TRY(cudaSetDevice(device));
+    DevLdl &m = o->d;
+    m.N = N; m.nA = (int)nA; m.nC = (int)nC;
+    CUDA_TRY(upload_sweep(o->ar, Wf, m.fwd));
+    CUDA_TRY(upload_sweep(o->ar, Wb, m.bwd));
+    CUDA_TRY(o->ar.upload(&m.b_d, bd));
+    CUDA_TRY(o->ar.upload(&m.b_partner, bpart));
+    CUDA_TRY(o->ar.upload(&m.b_e, be));
+    CUDA_TRY(o->ar.upload(&m.b_dp, bdp));
+    CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));
+    CUDA_TRY(o->ar.alloc(&m.ybuf, N, true));
+    CUDA_TRY(o->ar.alloc(&m.wflag, N, true));
+    CUDA_TRY(o->ar.alloc(&m.yflag, N, true));
+    CUDA_TRY(o->ar.alloc(&m.epoch, 1, true));
+    CUDA_TRY(upload_sell(o->ar, sKP, m.KP));
+    CUDA_TRY(upload_sell(o->ar, sK12, m.K12));
+    CUDA_TRY(upload_sell(o->ar, sK22, m.K22));
+    CUDA_TRY(o->ar.alloc(&m.atycy, N, true));                                   // opLDL2.m:90-91
+    CUDA_TRY(o->ar.alloc(&m.rvec, N, true));
+    CUDA_TRY(o->ar.alloc(&m.rnorm_out, 1, true));
+    m.nitref = 3; m.itref_tol = 1.0e-8; m.force_itref = 0; m.residual_update = 0;   // opLDL2.m:46-49
+    m.ru_stateful = 0; m.track_rnorm = 0;
+    CUDA_TRY(o->ar.alloc(&o->d_sys_alone, 1, true));
+    CUDA_TRY(o->ar.alloc(&o->d_z, N));
+    CUDA_TRY(o->ar.alloc(&o->d_y, N));
+    CUDA_TRY(o->ar.alloc(&o->d_status, 1, true));
+    o->nnz_off = Lrows.nnz(); o->lev_f = nlf; o->lev_b = nlb; o->n2x2 = n2;
+    *out = register_obj(std::move(o));
+    return CPK_OK;
+}
+
+static int ldl2_set(cpk_handle h, int which, double v)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "not an opLDL2 handle");
+    switch (which) {
+        case 0: M->d.nitref = (int)std::max(0.0, std::nearbyint(v)); break;         // opLDL2.m:97-99
+        case 1: M->d.itref_tol = v; break;     // the reference's setter is mis-spelt (opLDL2.m:101) and never runs: value taken as is
+        case 2: M->d.force_itref = (v != 0.0 && v != 1.0) ? 0 : (int)v; break;      // opLDL2.m:105-111
+        case 3: M->d.residual_update = v != 0.0; break;
+        case 4: M->d.ru_stateful = v != 0.0; break;
+        case 5: M->d.track_rnorm = v != 0.0; break;
+    }
+    return CPK_OK;
+}
+int cpk_ldl2_set_nitref(cpk_handle M, double v) { return ldl2_set(M, 0, v); }
+int cpk_ldl2_set_itref_tol(cpk_handle M, double v) { return ldl2_set(M, 1, v); }
+int cpk_ldl2_set_force_itref(cpk_handle M, int v) { return ldl2_set(M, 2, v); }
+int cpk_ldl2_set_residual_update(cpk_handle M, int v) { return ldl2_set(M, 3, v); }
+int cpk_ldl2_set_ru_stateful(cpk_handle M, int v) { return ldl2_set(M, 4, v); }
+int cpk_ldl2_set_track_rnorm(cpk_handle M, int v) { return ldl2_set(M, 5, v); }
+
+int cpk_ldl2_get_rnorm(cpk_handle h, double *rnorm)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M || !rnorm) return fail(CPK_ERR_ARG, "not an opLDL2 handle");
+    CUDA_TRY(cudaSetDevice(M->device));
+    CUDA_TRY(cudaMemcpy(rnorm, M->d.rnorm_out, sizeof(double), cudaMemcpyDeviceToHost));
+    return CPK_OK;
+}
+
+int cpk_ldl2_size(cpk_handle h, int64_t *N, int64_t *nA, int64_t *nC)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "not an opLDL2 handle");
+    if (N) *N = M->d.N;
+    if (nA) *nA = M->d.nA;
+    if (nC) *nC = M->d.nC;
+    return CPK_OK;
+}
+
+int cpk_ldl2_info(cpk_handle h, int64_t *nnz_L_off, int64_t *levels_fwd, int64_t *levels_bwd, int64_t *n_2x2)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "not an opLDL2 handle");
+    if (nnz_L_off) *nnz_L_off = M->nnz_off;
+    if (levels_fwd) *levels_fwd = M->lev_f;
+    if (levels_bwd) *levels_bwd = M->lev_b;
+    if (n_2x2) *n_2x2 = M->n2x2;
+    return CPK_OK;
+}
+
+static void fill_stats(cpk_stats *s, const DevStatus &d, float ms, int launches)
+{
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    s->niters = d.niters; s->solved = d.solved; s->status = d.status;
+    s->error_iter = d.err_iter; s->error_second = d.err_second; s->error_value = d.err_value;
+    s->hist_len = d.hist_len; s->napply = d.napply; s->nldlsolve = d.nldlsolve; s->nresid = d.nresid;
+    s->shifted = d.shifted; s->launches = launches; s->t_solve_ms = ms;
+    for (int i = 0; i < CPK_NPHASE; ++i) s->phase_cycles[i] = (double)d.phase_cycles[i];
+}
+
+static int status_to_rc(const DevStatus &d, int solver)
+{
+    if (d.err == 0) return CPK_OK;
+    if (d.err == CPK_ERR_INDEFINITE) {
+        const char *what = (solver == CPK_CPCGLANCZOS) ? "preconditioner not second-order sufficient"     // cpcglanczos.m:161,251
+                                                       : "preconditioner does not behave as a spd matrix."; // cpminres.m:138,198
+        return fail(CPK_ERR_INDEFINITE, "Iter %d, %sbeta (before sqrt) = %.5g : %s", d.err_iter,
+                    d.err_second ? "2nd Lanczos vec, " : "", d.err_value, what);
+    }
+    if (d.err == CPK_ERR_BREAKDOWN)
+        return fail(CPK_ERR_BREAKDOWN, "Iter %d, P-inner product = %.5g is negative under a square root "
+                    "(complex in the reference): preconditioner is not positive definite on the constraint null space",
+                    d.err_iter, d.err_value);
+    if (d.err == CPK_ERR_TIMEOUT) return fail(CPK_ERR_TIMEOUT, "device watchdog fired inside a wait loop");
+    return fail(d.err, "device error %d", d.err);
+}
+
+// launches a kernel for one team (grid: cooperative; cta: ordinary) and times it
+template <class KG, class KC>
+static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **params, size_t dsm, float *ms)
+{
+    CUDA_TRY(cudaMemsetAsync(dc->ctl, 0, sizeof(TeamCtl), dc->stream));
+    CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
+    if (grid)
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kgrid, dim3(dc->grid_blocks), dim3(kBlock), params, dsm, dc->stream));
+    else
+        CUDA_TRY(cudaLaunchKernel((const void *)kcta, dim3(1), dim3(kBlock), params, dsm, dc->stream));
+    ++g_launches;
+    CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    if (ms) CUDA_TRY(cudaEventElapsedTime(ms, dc->ev0, dc->ev1));
+    return CPK_OK;
+}
+
+int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_stats *stats)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M || !z || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_apply: bad handle or null vector");
+    DeviceCtx *dc;
+    int rc = get_device_ctx(M->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(M->device));
+    const int N = M->d.N;
+    DevSystem hs{};
+    hs.n = M->d.nA; hs.m = M->d.nC; hs.N = N; hs.M = M->d;
+    CUDA_TRY(cudaMemcpyAsync(M->d_sys_alone, &hs, sizeof hs, cudaMemcpyHostToDevice, dc->stream));
+    const double *dz = z; double *dy = y;
+    if (mem == CPK_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(M->d_z, z, sizeof(double) * N, cudaMemcpyHostToDevice, dc->stream));
+        dz = M->d_z; dy = M->d_y;
+    }
+    DevStatus *d_st = M->d_status;
+    CUDA_TRY(cudaMemsetAsync(d_st, 0, sizeof(DevStatus), dc->stream));
+    const DevSystem *ps = M->d_sys_alone;
+    void *params[] = {(void *)&ps, (void *)&dz, (void *)&dy, (void *)&d_st, (void *)&dc->ctl, (void *)&dc->partials};
+    float ms = 0.f;
+    rc = launch_team(dc, use_grid(N), k_apply<true>, k_apply<false>, params, 0, &ms);
+    if (rc) return rc;
+    if (mem == CPK_MEM_HOST) CUDA_TRY(cudaMemcpy(y, M->d_y, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(dc->h_status, d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost));
+    fill_stats(stats, dc->h_status[0], ms, 1);
+    return status_to_rc(dc->h_status[0], -1);
+}
+
+static int run_matvec(int device, const DevSell &A, const double *x, double *y, cpk_mem mem, cpk_stats *stats,
+                      double *stage_x, double *stage_y)
+{
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    const double *dx = x; double *dy = y;
+    if (mem == CPK_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(stage_x, x, sizeof(double) * A.ncols, cudaMemcpyHostToDevice, dc->stream));
+        dx = stage_x; dy = stage_y;
+    }
+    CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
+    const bool grid = use_grid(A.nrows);
+    if (grid) k_matvec<true><<<dc->grid_blocks, kBlock, 0, dc->stream>>>(A, dx, dy);
+    else      k_matvec<false><<<1, kBlock, 0, dc->stream>>>(A, dx, dy);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, dc->ev0, dc->ev1));
+    if (mem == CPK_MEM_HOST) CUDA_TRY(cudaMemcpy(y, stage_y, sizeof(double) * A.nrows, cudaMemcpyDeviceToHost));
+    if (stats) { memset(stats, 0, sizeof *stats); stats->t_solve_ms = ms; stats->launches = 1; }
+    return CPK_OK;
+}
+
+int cpk_ldl2_matvec(cpk_handle h, const double *b, double *y, cpk_mem mem, cpk_stats *stats)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M || !b || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_matvec: bad handle or null vector");
+    return run_matvec(M->device, M->d.KP, b, y, mem, stats, M->d_z, M->d_y);
+}
+
+// ---------------------------------------------------------------------------
+int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_handle Mh)
+{
+    if (!out) return fail(CPK_ERR_ARG, "cpk_system_create: null output handle");
+    Ldl2 *M = lookup<Ldl2>(Mh, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "cpk_system_create: M is not an opLDL2 handle");
+    if (!csc_ok(A) || !csc_ok(C)) return fail(CPK_ERR_ARG, "cpk_system_create: bad matrix");
+    if (A->nrows != A->ncols || C->nrows != C->ncols || A->nrows != M->d.nA || C->nrows != M->d.nC)
+        return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    if (M->in_system) return fail(CPK_ERR_ARG, "this opLDL2 handle already belongs to a system (its sweep buffers are not shareable)");
+    const int n = M->d.nA, m = M->d.nC;
+    DeviceCtx *dc;
+    int rc = get_device_ctx(M->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(M->device));
+    HCsr Hr = csr_from_csc(*A), Cr = csr_from_csc(*C);
+    // blkdiag(H, C) as one SELL matrix whose first slices are exactly H
+    HSell s;
+    s.nrows = n + m; s.ncols = n + m;
+    sell_append(s, Hr, 0, n, 0, 0);
+    const int h_slices = s.nslices, h_long = (int)s.lrow.size();
+    sell_append(s, Cr, 0, m, n, n);
+    if (s.sptr.empty()) s.sptr.push_back(0);
+    if (s.lptr.empty()) s.lptr.push_back(0);
+    if ((int64_t)s.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "H exceeds int32 indexing");
+    HSell sc = build_sell(Cr);
+    auto o = std::make_unique<System>();
+    o->device = M->device; o->ar.device = M->device; o->war.device = M->device;
+    o->M = M; o->M_handle = Mh;
+    DevSystem &d = o->h;
+    d.n = n; d.m = m; d.N = n + m;
+    CUDA_TRY(upload_sell(o->ar, s, d.HC));
+    d.Hn = d.HC; d.Hn.nrows = n; d.Hn.ncols = n; d.Hn.nslices = h_slices; d.Hn.nlong = h_long;
+    CUDA_TRY(upload_sell(o->ar, sc, d.Cm));
+    d.M = M->d;
+    CUDA_TRY(o->ar.alloc(&o->d_sys, 1));
+    CUDA_TRY(o->ar.alloc(&o->d_args, 1));
+    CUDA_TRY(o->ar.alloc(&o->d_status, 1, true));
+    CUDA_TRY(o->ar.alloc(&o->d_b, d.N));
+    CUDA_TRY(o->ar.alloc(&o->d_x, d.N));
+    M->in_system = true;
+    *out = register_obj(std::move(o));
+    return CPK_OK;
+}
+
+int cpk_system_matvec(cpk_handle h, int which, const double *x, double *y, cpk_mem mem, cpk_stats *stats)
+{
+    System *S = lookup<System>(h, OBJ_SYSTEM);
+    if (!S || !x || !y || which < 0 || which > 1) return fail(CPK_ERR_ARG, "cpk_system_matvec: bad argument");
+    return run_matvec(S->device, which == 0 ? S->h.Hn : S->h.Cm, x, y, mem, stats, S->d_b, S->d_x);
+}
+
+void cpk_opts_default(cpk_opts *o, int solver, int64_t n, int64_t m)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->atol = 1.0e-6; o->rtol = 1.0e-6; o->btol = 0.0;
+    o->itmax = (solver == CPK_CPGMRES || solver == CPK_CPDQGMRES) ? n + m : n;
+    o->restart = 50; o->mem = 50; o->profile = 0;
+}
+
+int64_t cpk_hist_capacity(int solver, const cpk_opts *o)
+{
+    if (!o) return 0;
+    int64_t cap = o->itmax + 2;
+    if (solver == CPK_CPGMRES) {
+        const int64_t R = std::max(1, o->restart);
+        cap = ((o->itmax + R - 1) / R) * R + 2;                 // cpgmres.m:148: may overshoot itmax
+    }
+    return std::max<int64_t>(cap, 2);
+}
+
+struct Plan {
+    int nvec;               // N-vectors of workspace incl. the 2 reserved
+    size_t dsm;             // dynamic shared bytes
+    long long gs;           // global scalar scratch doubles
+    int wide_cols;
+    int restart, mem;
+};
+
+static int make_plan(int solver, const cpk_opts *o, Plan *p)
+{
+    p->dsm = 0; p->gs = 0; p->wide_cols = 0; p->restart = 1; p->mem = 1;
+    switch (solver) {
+        case CPK_CPCG: p->nvec = 4; break;
+        case CPK_CPCGLANCZOS: p->nvec = 6; break;
+        case CPK_CPMINRES: p->nvec = 8; break;
+        case CPK_CPSYMMLQ: p->nvec = 6; break;
+        case CPK_CPGMRES: {
+            if (o->restart < 1) return fail(CPK_ERR_ARG, "restart must be >= 1");
+            const int R = o->restart;
+            if (R > 2048) return fail(CPK_ERR_UNSUPPORTED, "restart > 2048 is not supported");
+            p->restart = R;
+            p->nvec = 2 + R + 1;
+            p->dsm = sizeof(double) * (5 * (size_t)R + 2) + sizeof(int) * ((size_t)R + 2);
+            p->gs = (long long)(R + 1) * R + R;
+            p->wide_cols = R + 1;
+            break;
+        }
+        case CPK_CPDQGMRES: {
+            int mem = std::max(1, o->mem);                                          // cpdqgmres.m:117
+            mem = (int)std::max<int64_t>(1, std::min<int64_t>(mem, o->itmax));      // cpdqgmres.m:125
+            p->mem = mem;
+            p->nvec = 2 + 2 * (mem + 1);
+            p->dsm = sizeof(double) * (5 * (size_t)mem + 3 + (size_t)(mem + 2) * (mem + 3)) + sizeof(int) * ((size_t)mem + 2);
+            if (p->dsm > 190 * 1024) return fail(CPK_ERR_UNSUPPORTED, "mem = %d needs %zu B of shared memory for the H band (max ~150)", mem, p->dsm);
+            p->wide_cols = mem + 1;
+            break;
+        }
+        default: return fail(CPK_ERR_ARG, "unknown solver id %d", solver);
+    }
+    p->nvec += 2;
+    p->dsm = (p->dsm + 15) & ~(size_t)15;
+    return CPK_OK;
+}
+
+static int ensure_buffers(System *S, const Plan &p, int64_t hist_cap)
+{
+    const long long need = (long long)p.nvec * S->h.N;
+    if (need > S->work_len || hist_cap * 3 > S->hist_cap || p.gs > S->gs_len) {
+        S->war.release();
+        S->d_work = nullptr; S->d_hist = nullptr; S->d_gs = nullptr;
+        S->work_len = std::max(need, S->work_len);
+        S->hist_cap = std::max<long long>(hist_cap * 3, S->hist_cap);
+        S->gs_len = std::max<long long>(p.gs, S->gs_len);
+        CUDA_TRY(S->war.alloc(&S->d_work, (size_t)S->work_len));
+        CUDA_TRY(S->war.alloc(&S->d_hist, (size_t)S->hist_cap));
+        CUDA_TRY(S->war.alloc(&S->d_gs, (size_t)std::max<long long>(S->gs_len, 1)));
+    }
+    return CPK_OK;
+}
+
+static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *opts, double *x_out, double *dy_out,
+                    cpk_mem mem, cpk_stats *stats, double *hist, int64_t hist_cap, int reg_mode)
+{
+    System *S = lookup<System>(h, OBJ_SYSTEM);
+    if (!S) return fail(CPK_ERR_ARG, "not a system handle");
+    if (!b || !x_out || !opts) return fail(CPK_ERR_ARG, "reg_cpkrylov: not enough inputs");       // reg_cpkrylov.m:122-125
+    if (opts->itmax < 0) return fail(CPK_ERR_ARG, "itmax must be >= 0");
+    Plan plan;
+    int rc = make_plan(solver, opts, &plan);
+    if (rc) return rc;
+    DeviceCtx *dc;
+    rc = get_device_ctx(S->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(S->device));
+    const int n = S->h.n, m = S->h.m, N = S->h.N;
+    const int64_t cap = cpk_hist_capacity(solver, opts);
+    rc = ensure_buffers(S, plan, cap);
+    if (rc) return rc;
+    const bool grid = use_grid(N);
+    if (grid && plan.wide_cols) { rc = ensure_wide(dc, plan.wide_cols); if (rc) return rc; }
+
+    S->h.M = S->M->d;           // pick up option changes made through the opLDL2 setters
+    CUDA_TRY(cudaMemcpyAsync(S->d_sys, &S->h, sizeof(DevSystem), cudaMemcpyHostToDevice, dc->stream));
+    SolveArgs a{};
+    a.solver = solver; a.reg_mode = reg_mode;
+    const int nb = reg_mode ? N : n;
+    if (mem == CPK_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(S->d_b, b, sizeof(double) * nb, cudaMemcpyHostToDevice, dc->stream));
+        a.b = S->d_b; a.x = S->d_x;
+    } else {
+        a.b = b;
+        a.x = (reg_mode || !dy_out || dy_out == x_out + n) ? x_out : S->d_x;
+    }
+    a.atol = opts->atol; a.rtol = opts->rtol; a.btol = opts->btol; a.itmax = opts->itmax;
+    a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
+    a.work = S->d_work; a.work_len = (long long)plan.nvec * N;
+    a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+    CUDA_TRY(cudaMemcpyAsync(S->d_args, &a, sizeof a, cudaMemcpyHostToDevice, dc->stream));
+    CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
+    const DevSystem *ps = S->d_sys; const SolveArgs *pa = S->d_args;
+    double *wide = dc->wide; int wide_cols = dc->wide_cols;
+    void *params[] = {(void *)&ps, (void *)&pa, (void *)&dc->ctl, (void *)&dc->partials, (void *)&wide, (void *)&wide_cols};
+    float ms = 0.f;
+    rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, plan.dsm, &ms);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(dc->h_status, S->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost));
+    const DevStatus &st = dc->h_status[0];
+    if (mem == CPK_MEM_HOST) {
+        if (reg_mode) CUDA_TRY(cudaMemcpy(x_out, S->d_x, sizeof(double) * N, cudaMemcpyDeviceToHost));
+        else {
+            CUDA_TRY(cudaMemcpy(x_out, S->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost));
+            if (dy_out) CUDA_TRY(cudaMemcpy(dy_out, S->d_x + n, sizeof(double) * m, cudaMemcpyDeviceToHost));
+        }
+    } else if (a.x == S->d_x) {
+        CUDA_TRY(cudaMemcpy(x_out, S->d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        if (dy_out) CUDA_TRY(cudaMemcpy(dy_out, S->d_x + n, sizeof(double) * m, cudaMemcpyDeviceToDevice));
+    }
+    if (hist && hist_cap > 0) {
+        const int rows = solver == CPK_CPSYMMLQ ? 3 : 1;
+        const int64_t len = std::min<int64_t>(std::min<int64_t>(st.hist_len, cap), hist_cap);
+        for (int r = 0; r < rows; ++r)
+            if (len > 0)
+                CUDA_TRY(cudaMemcpy(hist + (size_t)r * hist_cap, S->d_hist + (size_t)r * cap, sizeof(double) * len, cudaMemcpyDeviceToHost));
+    }
+    fill_stats(stats, st, ms, 1);
+    return status_to_rc(st, solver);
+}
+
+int cpk_solve(cpk_handle S, int solver, const double *b1, const cpk_opts *opts, double *dx, double *dy, cpk_mem mem,
+              cpk_stats *stats, double *hist, int64_t hist_cap)
+{
+    return do_solve(S, solver, b1, opts, dx, dy, mem, stats, hist, hist_cap, 0);
+}
+
+int cpk_reg_solve(cpk_handle S, int solver, const double *b, const cpk_opts *opts, double *x, cpk_mem mem,
+                  cpk_stats *stats, double *hist, int64_t hist_cap)
+{
+    return do_solve(S, solver, b, opts, x, nullptr, mem, stats, hist, hist_cap, 1);
+}
+
+// ---------------------------------------------------------------------------
+// batch: one CTA per system, one launch
+// ---------------------------------------------------------------------------
+int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,
+                        double *const *x, cpk_stats *stats, double *const *hist, int64_t hist_cap)
+{
+    if (!handles || count <= 0 || !b || !x || !opts) return fail(CPK_ERR_ARG, "cpk_batch_reg_solve: bad argument");
+    if (count > kMaxBatch) return fail(CPK_ERR_UNSUPPORTED, "batch larger than %d systems: split it", kMaxBatch);
+    Plan plan;
+    int rc = make_plan(solver, opts, &plan);
+    if (rc) return rc;
+    std::vector<System *> sys(count);
+    for (int64_t i = 0; i < count; ++i) {
+        sys[i] = lookup<System>(handles[i], OBJ_SYSTEM);
+        if (!sys[i]) return fail(CPK_ERR_ARG, "batch entry %lld is not a system handle", (long long)i);
+        if (sys[i]->device != sys[0]->device) return fail(CPK_ERR_ARG, "all systems of a batch must live on one device");
+        for (int64_t j = 0; j < i; ++j)
+            if (sys[j] == sys[i]) return fail(CPK_ERR_ARG, "system %lld appears twice in the batch", (long long)i);
+    }
+    DeviceCtx *dc;
+    rc = get_device_ctx(sys[0]->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(sys[0]->device));
+    const int64_t cap = cpk_hist_capacity(solver, opts);
+    std::vector<DevSystem> hsys(count);
+    std::vector<SolveArgs> hargs(count);
+    for (int64_t i = 0; i < count; ++i) {
+        System *S = sys[i];
+        rc = ensure_buffers(S, plan, cap);
+        if (rc) return rc;
+        S->h.M = S->M->d;
+        hsys[i] = S->h;
+        SolveArgs a{};
+        a.solver = solver; a.reg_mode = 1;
+        CUDA_TRY(cudaMemcpyAsync(S->d_b, b[i], sizeof(double) * S->h.N, cudaMemcpyHostToDevice, dc->stream));
+        a.b = S->d_b; a.x = S->d_x;
+        a.atol = opts->atol; a.rtol = opts->rtol; a.btol = opts->btol; a.itmax = opts->itmax;
+        a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
+        a.work = S->d_work; a.work_len = (long long)plan.nvec * S->h.N;
+        a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+        hargs[i] = a;
+        CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
+    }
+    DevSystem *d_sys = nullptr; SolveArgs *d_args = nullptr;
+    CUDA_TRY(cudaMalloc(&d_sys, sizeof(DevSystem) * count));
+    CUDA_TRY(cudaMalloc(&d_args, sizeof(SolveArgs) * count));
+    CUDA_TRY(cudaMemcpyAsync(d_sys, hsys.data(), sizeof(DevSystem) * count, cudaMemcpyHostToDevice, dc->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_args, hargs.data(), sizeof(SolveArgs) * count, cudaMemcpyHostToDevice, dc->stream));
+    CUDA_TRY(cudaMemsetAsync(dc->ctl, 0, sizeof(TeamCtl) * count, dc->stream));
+    CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
+    {
+        double *nullp = nullptr; int zero = 0;
+        void *params[] = {(void *)&d_sys, (void *)&d_args, (void *)&dc->ctl, (void *)&nullp, (void *)&nullp, (void *)&zero};
+        CUDA_TRY(cudaLaunchKernel(solver_kernel(solver, false), dim3((unsigned)count), dim3(kBlock), params, plan.dsm, dc->stream));
+    }
+    ++g_launches;
+    CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, dc->ev0, dc->ev1));
+    cudaFree(d_sys); cudaFree(d_args);
+    int first_rc = CPK_OK;
+    std::string first_msg;
+    for (int64_t i = 0; i < count; ++i) {
+        System *S = sys[i];
+        CUDA_TRY(cudaMemcpy(&dc->h_status[i], S->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(x[i], S->d_x, sizeof(double) * S->h.N, cudaMemcpyDeviceToHost));
+        const DevStatus &st = dc->h_status[i];
+        if (hist && hist[i] && hist_cap > 0) {
+            const int rows = solver == CPK_CPSYMMLQ ? 3 : 1;
+            const int64_t len = std::min<int64_t>(std::min<int64_t>(st.hist_len, cap), hist_cap);
+            for (int r = 0; r < rows; ++r)
+                if (len > 0)
+                    CUDA_TRY(cudaMemcpy(hist[i] + (size_t)r * hist_cap, S->d_hist + (size_t)r * cap, sizeof(double) * len, cudaMemcpyDeviceToHost));
+        }
+        if (stats) fill_stats(&stats[i], st, ms, i == 0 ? 1 : 0);
+        const int r = status_to_rc(st, solver);
+        if (r && !first_rc) { first_rc = r; first_msg = "system " + std::to_string(i) + ": " + g_err; }
+    }
+    if (first_rc) { g_err = first_msg; return first_rc; }
+    return CPK_OK;
+}
+
+int cpk_destroy(cpk_handle h)
+{
+    std::unique_ptr<Object> victim;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_obj.find(h);
+        if (it == g_obj.end()) return fail(CPK_ERR_ARG, "unknown handle");
+        if (it->second->kind == OBJ_LDL2 && static_cast<Ldl2 *>(it->second.get())->in_system)
+            return fail(CPK_ERR_ARG, "opLDL2 handle is still owned by a system; destroy the system first");
+        if (it->second->kind == OBJ_SYSTEM) static_cast<System *>(it->second.get())->M->in_system = false;
+        victim = std::move(it->second);
+        g_obj.erase(it);
+    }
+    return CPK_OK;
+}
+
+int cpk_destroy_all(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    // systems first (they reference their opLDL2)
+    for (auto it = g_obj.begin(); it != g_obj.end();)
+        if (it->second->kind == OBJ_SYSTEM) it = g_obj.erase(it); else ++it;
+    g_obj.clear();
+    return CPK_OK;
+}
+

@@ -1,0 +1,4 @@
+// Translation unit of the persistent cpcg kernel (kernels/cpcg.m of the reference):
+// compiled on its own so the six solvers build in parallel.
+#include "cpk_solvers.cuh"
+CPK_DEFINE_SOLVER_TU(0, cpcg)

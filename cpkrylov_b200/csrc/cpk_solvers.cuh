@@ -1,0 +1,808 @@
+// cpk_solvers.cuh -- the six constraint-preconditioned Krylov loops of cpkrylov,
+// each as ONE device function that runs the whole `while` on the GPU: no host
+// round trip per iteration, scalars recomputed redundantly (bit-identically) by
+// every thread from team-wide deterministic reductions.
+//
+// Vector convention: every Krylov vector is stored as one N-vector [v; q]
+// (n-part, then m-part); H and C are applied together as blkdiag(H, C).
+// Statement order and association follow the reference line by line; the file
+// is compiled with -fmad=false so a*b+c is rounded twice as in MATLAB.
+#pragma once
+#include "cpk_kernels.cuh"
+
+namespace cpk {
+
+constexpr double kEps = 2.220446049250313e-16;
+
+template <class Team>
+struct Ctx {
+    Team &T;
+    const DevSystem &S;
+    const SolveArgs &A;
+    DevStatus *st;
+    PhaseClock pc;
+    int epoch;
+    double *dsm;            // dynamic shared memory (doubles)
+    int n, m, N;
+
+    __device__ double *vec(int i) const { return A.work + (size_t)i * N; }
+    __device__ void hist(int row, long long idx, double v) const {
+        if (T.leader() && A.hist && idx < A.hist_cap) A.hist[(size_t)row * A.hist_cap + idx] = v;
+    }
+    __device__ void fail(int code, int iter, double val, int second = 0) const {
+        if (T.leader()) { st->err = code; st->err_iter = iter; st->err_value = val; st->err_second = second; }
+    }
+    // U = blkdiag(H,C) * V with alpha = U'V fused (e.g. cpminres.m:187-189)
+    __device__ double spmv_dot(const double *V, double *U) {
+        pc.mark(CPK_PH_VEC_);
+        double part[1] = {0.0};
+        spmv_sell(T, S.HC, V, [&](int row, double s) { U[row] = s; part[0] += s * V[row]; });
+        T.template reduce<1>(part);
+        pc.mark(CPK_PH_SPMV_);
+        return part[0];
+    }
+    __device__ void apply(const double *z, bool neg_tail, double *y) {
+        VecIn in{z, nullptr, n, neg_tail};
+        ldl2_apply(T, S.M, in, y, epoch, st, pc);
+    }
+};
+
+__device__ __forceinline__ double dsign(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0); }
+
+// util/SymGivens.m:1-29
+__device__ __forceinline__ void sym_givens(double a, double b, double &c, double &s, double &d)
+{
+    if (b == 0.0) {
+        c = (a == 0.0) ? 1.0 : dsign(a);
+        s = 0.0;
+        d = fabs(a);
+    } else if (a == 0.0) {
+        c = 0.0;
+        s = dsign(b);
+        d = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        const double t = a / b;
+        s = dsign(b) / sqrt(1.0 + t * t);
+        c = s * t;
+        d = b / s;
+    } else {
+        const double t = b / a;
+        c = dsign(a) / sqrt(1.0 + t * t);
+        s = c * t;
+        d = a / c;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpcg.m:118-193
+// work vectors: 0 X=[x;a] 1 GW=[g;w] 2 PQ=[p;q] 3 APCQ 4 RU
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    double *GW = c.vec(0), *PQ = c.vec(1), *APCQ = c.vec(2), *RU = c.vec(3);
+    TEAM_FOR(T, i, N) { X[i] = 0.0; GW[i] = (i < n) ? -b[i] : 0.0; }
+    T.sync();
+    c.apply(GW, false, RU);                                         // :125
+    double part[1] = {0.0};
+    TEAM_FOR(T, i, N) { PQ[i] = -RU[i]; if (i < n) part[0] += GW[i] * RU[i]; }
+    T.template reduce<1>(part);                                     // also publishes PQ
+    double rn2 = part[0];                                           // :130
+    if (rn2 < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, 0, rn2); return; }
+    double residNorm = sqrt(rn2);
+    const double stopTol = c.A.atol + c.A.rtol * residNorm;
+    c.hist(0, 0, residNorm);
+    long long itn = 0;
+    while (residNorm > stopTol && itn < c.A.itmax) {                // :147
+        ++itn;
+        const double pAp_qCq = c.spmv_dot(PQ, APCQ);                // :151-152
+        const double alpha = rn2 / pAp_qCq;                         // :154
+        TEAM_FOR(T, i, N) {                                         // :161-164
+            X[i] = X[i] + alpha * PQ[i];
+            GW[i] = GW[i] + alpha * APCQ[i];
+        }
+        T.sync();
+        c.apply(GW, false, RU);                                     // :166
+        part[0] = 0.0;
+        TEAM_FOR(T, i, N) {                                         // :167-168
+            if (i < n) part[0] += GW[i] * RU[i];
+            else { const double t = X[i] + RU[i]; part[0] += t * GW[i]; }
+        }
+        T.template reduce<1>(part);
+        const double rn2_new = part[0];
+        const double beta = rn2_new / rn2;                          // :169
+        TEAM_FOR(T, i, N) {                                         // :171-172
+            const double t = (i < n) ? RU[i] : X[i] + RU[i];
+            PQ[i] = -t + beta * PQ[i];
+        }
+        rn2 = rn2_new;
+        if (rn2 < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)itn, rn2); break; }
+        residNorm = sqrt(rn2);
+        c.hist(0, itn, residNorm);
+        T.sync();
+        c.pc.mark(CPK_PH_VEC_);
+    }
+    if (T.leader()) {
+        c.st->niters = itn; c.st->hist_len = itn + 1;
+        c.st->solved = residNorm <= stopTol;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Lanczos pieces shared by cpcglanczos / cpminres / cpsymmlq
+// ---------------------------------------------------------------------------
+// v1, q1 and beta1^2 (cpminres.m:131-134): VKP1 = [vprec1; -vprec2], returns u'v1
+template <class Team>
+__device__ double lanczos_start(Ctx<Team> &c, const double *b, double *U, double *VPREC, double *VKP1)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    TEAM_FOR(T, i, N) U[i] = (i < n) ? b[i] : 0.0;
+    T.sync();
+    c.apply(U, false, VPREC);
+    double part[1] = {0.0};
+    TEAM_FOR(T, i, N) {
+        const double v = (i < n) ? VPREC[i] : -VPREC[i];
+        VKP1[i] = v;
+        if (i < n) part[0] += U[i] * v;
+    }
+    T.template reduce<1>(part);
+    return part[0];
+}
+
+// u = A vk, t = C qk, alpha, vprec = M[u;-t], unnormalised v_{k+1}, q_{k+1} and
+// beta^2 = u'v_{k+1} + t'q_{k+1}   (cpminres.m:187-194).  VKM1 == nullptr drops
+// the beta*v_{k-1} term (cpsymmlq.m:202-204).
+template <class Team>
+__device__ void lanczos_step(Ctx<Team> &c, const double *VK, const double *VKM1, double beta,
+                             double *U, double *VPREC, double *VKP1, double &alpha, double &betasq)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    alpha = c.spmv_dot(VK, U);
+    c.apply(U, true, VPREC);
+    double part[1] = {0.0};
+    if (VKM1) {
+        TEAM_FOR(T, i, N) {
+            double v;
+            if (i < n) v = VPREC[i] - alpha * VK[i] - beta * VKM1[i];
+            else { v = VK[i] - VPREC[i]; v = v - alpha * VK[i] - beta * VKM1[i]; }
+            VKP1[i] = v;
+            part[0] += U[i] * v;
+        }
+    } else {
+        TEAM_FOR(T, i, N) {
+            double v;
+            if (i < n) v = VPREC[i] - alpha * VK[i];
+            else { v = VK[i] - VPREC[i]; v = v - alpha * VK[i]; }
+            VKP1[i] = v;
+            part[0] += U[i] * v;
+        }
+    }
+    T.template reduce<1>(part);
+    betasq = part[0];
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpminres.m:114-252
+// work: 0 U 1 VPREC 2..4 Lanczos ring 5..7 W ring
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpminres(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    double *U = c.vec(0), *VPREC = c.vec(1);
+    double *VKM1 = c.vec(2), *VK = c.vec(3), *VKP1 = c.vec(4);
+    double *WV1 = c.vec(5), *WV2 = c.vec(6), *WV = c.vec(7);
+    const double eps100 = 100.0 * kEps;
+
+    double beta = lanczos_start(c, b, U, VPREC, VKP1);
+    if (beta < -eps100) { c.fail(CPK_ERR_INDEFINITE_, 0, beta); return; }
+    beta = sqrt(fabs(beta));
+    TEAM_FOR(T, i, N) {
+        X[i] = 0.0; VK[i] = 0.0; WV2[i] = 0.0;
+        double v = VKP1[i];
+        if (beta > 0.0) v = v / beta;
+        VKP1[i] = v; WV[i] = v;
+    }
+    T.sync();
+    double residNorm = beta;
+    c.hist(0, 0, residNorm);
+    long long k = 0;
+    double deltabar = 0.0, epsln = 0.0, taubar = beta, cs = -1.0, sn = 0.0;
+    const double stopTol = c.A.atol + c.A.rtol * residNorm;
+
+    while (residNorm > stopTol && k < c.A.itmax) {                  // :176
+        ++k;
+        { double *t = VKM1; VKM1 = VK; VK = VKP1; VKP1 = t; }       // :181-184
+        double alpha, betasq;
+        lanczos_step(c, VK, VKM1, beta, U, VPREC, VKP1, alpha, betasq);
+        if (betasq < -eps100) { c.fail(CPK_ERR_INDEFINITE_, (int)k, betasq); break; }
+        beta = sqrt(fabs(betasq));
+        const double oldeps = epsln;                                // :211-215
+        const double delta = cs * deltabar + sn * alpha;
+        const double gammabar = sn * deltabar - cs * alpha;
+        epsln = sn * beta;
+        deltabar = -cs * beta;
+        const double gamma = hypot(gammabar, beta);                 // :218
+        cs = gammabar / gamma;
+        sn = beta / gamma;
+        const double tau = cs * taubar;
+        taubar = sn * taubar;
+        { double *t = WV1; WV1 = WV2; WV2 = WV; WV = t; }           // :225-228
+        TEAM_FOR(T, i, N) {
+            if (beta > 0.0) VKP1[i] = VKP1[i] / beta;               // :203-204
+            const double w = (VK[i] - oldeps * WV1[i] - delta * WV2[i]) / gamma;
+            WV[i] = w;
+            X[i] = (i < n) ? X[i] + tau * w : X[i] - tau * w;       // :231-232
+        }
+        residNorm = taubar;
+        c.hist(0, k, residNorm);
+        T.sync();
+        c.pc.mark(CPK_PH_VEC_);
+    }
+    if (T.leader()) { c.st->niters = k; c.st->hist_len = k + 1; c.st->solved = residNorm <= stopTol; }
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpcglanczos.m:135-325
+// work: 0 U 1 VPREC 2..4 Lanczos ring 5 WV
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpcglanczos(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    double *U = c.vec(0), *VPREC = c.vec(1);
+    double *VKM1 = c.vec(2), *VK = c.vec(3), *VKP1 = c.vec(4), *WV = c.vec(5);
+    const double eps100 = 100.0 * kEps;
+    const double btol = c.A.btol;
+
+    double beta = lanczos_start(c, b, U, VPREC, VKP1);
+    if (beta < -eps100) { c.fail(CPK_ERR_INDEFINITE_, 0, beta); return; }
+    beta = sqrt(fabs(beta));
+    TEAM_FOR(T, i, N) {
+        X[i] = 0.0; VK[i] = 0.0;
+        double v = VKP1[i];
+        if (beta > 0.0) v = v / beta;
+        VKP1[i] = v; WV[i] = v;
+    }
+    T.sync();
+    const double beta1 = beta;
+    double residNorm = beta1;
+    c.hist(0, 0, residNorm);
+    long long k = 0;
+    double dg = 0.0, low = 1.0, eta = beta, oldbeta = 0.0, opNorm2 = 0.0;
+    double rhobar = 1.0, xxNorm2 = 0.0, xNorm = 0.0, tau = 0.0, delta = 0.0;
+    const double stopTol = c.A.atol + c.A.rtol * residNorm;
+    double bstopTol = btol * beta1;
+
+    while (residNorm > stopTol && residNorm > bstopTol && k < c.A.itmax) {      // :221
+        ++k;
+        { double *t = VKM1; VKM1 = VK; VK = VKP1; VKP1 = t; }
+        double alpha, betasq;
+        lanczos_step(c, VK, VKM1, beta, U, VPREC, VKP1, alpha, betasq);
+        dg = alpha - low * low * dg;                                            // :236
+        const double zeta = eta / dg;
+        if (betasq < -eps100) { c.fail(CPK_ERR_INDEFINITE_, (int)k, betasq); break; }
+        beta = sqrt(fabs(betasq));
+        low = beta / dg;                                                        // :265
+        eta = -low * eta;
+        TEAM_FOR(T, i, N) {
+            const double w = WV[i];
+            X[i] = (i < n) ? X[i] + zeta * w : X[i] - zeta * w;                 // :238-239
+            double v = VKP1[i];
+            if (beta > 0.0) { v = v / beta; VKP1[i] = v; }                      // :258-259
+            WV[i] = v - low * w;                                                // :267-268
+        }
+        if (btol > 0.0) {                                                       // :271-291
+            const double rho = sqrt(rhobar * rhobar + low * low);
+            const double cs = rhobar / rho;
+            const double sn = low / rho;
+            const double num = zeta - delta * tau;
+            const double taub = num / rhobar;
+            tau = num / rho;
+            xNorm = sqrt(xxNorm2 + taub * taub);
+            xxNorm2 = xxNorm2 + tau * tau;
+            delta = sn;
+            rhobar = -cs;
+            opNorm2 = opNorm2 + alpha * alpha + beta * beta + oldbeta * oldbeta;
+            const double opNorm = sqrt(opNorm2);
+            const double bkerr = opNorm * xNorm + beta1;
+            bstopTol = btol * bkerr;
+        }
+        residNorm = beta * fabs(zeta);                                          // :293
+        c.hist(0, k, residNorm);
+        oldbeta = beta;
+        T.sync();
+        c.pc.mark(CPK_PH_VEC_);
+    }
+    if (T.leader()) {
+        c.st->niters = k; c.st->hist_len = k + 1;
+        int solved = 0, status = 0;
+        if (residNorm <= stopTol) { solved = 1; status = 1; }
+        if (btol > 0.0 && residNorm <= bstopTol) { solved = 1; status = 2; }
+        c.st->solved = solved; c.st->status = status;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpsymmlq.m:121-367
+// work: 0 U 1 VPREC 2..4 Lanczos ring 5 WV
+// hist rows: 0 cg, 1 lq, 2 qr
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpsymmlq(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    double *U = c.vec(0), *VPREC = c.vec(1);
+    double *VKM1 = c.vec(2), *VK = c.vec(3), *VKP1 = c.vec(4), *WV = c.vec(5);
+    const double eps100 = 100.0 * kEps;
+
+    double beta1 = lanczos_start(c, b, U, VPREC, VKP1);
+    if (beta1 < -eps100) { c.fail(CPK_ERR_INDEFINITE_, 0, beta1); return; }
+    beta1 = sqrt(fabs(beta1));
+    TEAM_FOR(T, i, N) {
+        X[i] = 0.0; WV[i] = 0.0;
+        if (beta1 > 0.0) VKP1[i] = VKP1[i] / beta1;
+    }
+    T.sync();
+    double cgresidNorm = beta1;
+    const double stopTol = c.A.atol + c.A.rtol * cgresidNorm;
+    long long k = 0;
+    long long hlen;
+    if (cgresidNorm <= stopTol) {                                               // :161-166
+        c.hist(0, 0, beta1); c.hist(1, 0, beta1); c.hist(2, 0, beta1);
+        hlen = 1;
+    } else {
+        { double *t = VK; VK = VKP1; VKP1 = t; }                                // :194-195
+        double alpha, betasq;
+        lanczos_step(c, VK, (const double *)nullptr, 0.0, U, VPREC, VKP1, alpha, betasq);
+        if (betasq < -eps100) { c.fail(CPK_ERR_INDEFINITE_, 0, betasq, 1); return; }
+        double beta = sqrt(fabs(betasq));
+        if (beta > 0.0) { TEAM_FOR(T, i, N) VKP1[i] = VKP1[i] / beta; }
+        T.sync();
+        double gammabar = alpha, deltabar = beta, epsdelzeta = beta1, epsilonzeta = 0.0;
+        double bstep = 0.0, snprod = 1.0, matnorm2 = alpha * alpha + beta * beta;
+        double lqresidNorm, qrresidNorm, den;
+        c.hist(0, 0, beta1);                                                    // :331 (prepended)
+        long long h = 0;                                                        // entries in lq/qr rows
+        while (cgresidNorm > stopTol && k < c.A.itmax) {                        // :229
+            double matnorm = sqrt(matnorm2);
+            double epsmat = matnorm * kEps;
+            den = gammabar;
+            if (den == 0.0) den = epsmat;
+            lqresidNorm = hypot(epsdelzeta, epsilonzeta);
+            qrresidNorm = snprod * beta1;
+            cgresidNorm = qrresidNorm * beta / fabs(den);
+            c.hist(1, h, lqresidNorm); c.hist(2, h, qrresidNorm); c.hist(0, h + 1, cgresidNorm);
+            ++h;
+            ++k;
+            { double *t = VKM1; VKM1 = VK; VK = VKP1; VKP1 = t; }
+            const double betaold = beta;
+            lanczos_step(c, VK, VKM1, beta, U, VPREC, VKP1, alpha, betasq);
+            if (betasq < -eps100) { c.fail(CPK_ERR_INDEFINITE_, (int)k, betasq); return; }
+            beta = sqrt(fabs(betasq));
+            matnorm2 = matnorm2 + alpha * alpha + beta * beta + betaold * betaold;
+            const double gamma = hypot(gammabar, betaold);                      // :291-297
+            const double cs = gammabar / gamma;
+            const double sn = betaold / gamma;
+            const double delta = cs * deltabar + sn * alpha;
+            gammabar = sn * deltabar - cs * alpha;
+            const double epsilon = sn * beta;
+            deltabar = -cs * beta;
+            const double zeta = epsdelzeta / gamma;                             // :300-306
+            const double zcs = zeta * cs;
+            const double zsn = zeta * sn;
+            TEAM_FOR(T, i, N) {
+                if (beta > 0.0) VKP1[i] = VKP1[i] / beta;
+                const double w = WV[i], v = VK[i];
+                X[i] = (i < n) ? X[i] + zcs * w + zsn * v : X[i] - zcs * w - zsn * v;
+                WV[i] = sn * w - cs * v;
+            }
+            bstep = bstep + snprod * cs * zeta;                                 // :310-313
+            snprod = snprod * sn;
+            epsdelzeta = epsilonzeta - delta * zeta;
+            epsilonzeta = -epsilon * zeta;
+            T.sync();
+            c.pc.mark(CPK_PH_VEC_);
+        }
+        {                                                                       // :318-327
+            double matnorm = sqrt(matnorm2);
+            double epsmat = matnorm * kEps;
+            den = gammabar;
+            if (den == 0.0) den = epsmat;
+            lqresidNorm = hypot(epsdelzeta, epsilonzeta);
+            qrresidNorm = snprod * beta1;
+            c.hist(1, h, lqresidNorm); c.hist(2, h, qrresidNorm);
+            ++h;
+        }
+        hlen = h;
+        double zetabar = 0.0;
+        const bool to_cg = cgresidNorm < lqresidNorm;                           // :334
+        if (to_cg) { zetabar = epsdelzeta / den; bstep = bstep + snprod * zetabar; }
+        // :342-347  one more apply, M*[b;0]
+        TEAM_FOR(T, i, N) U[i] = (i < n) ? b[i] : 0.0;
+        T.sync();
+        c.apply(U, false, VPREC);
+        bstep = bstep / beta1;
+        TEAM_FOR(T, i, N) {
+            double xi = X[i];
+            if (to_cg) xi = (i < n) ? xi + zetabar * WV[i] : xi - zetabar * WV[i];
+            // vk = vprec1, qk = -vprec2:  x + bstep*vk ;  y - bstep*qk
+            xi = (i < n) ? xi + bstep * VPREC[i] : xi - bstep * (-VPREC[i]);
+            X[i] = xi;
+        }
+    }
+    if (T.leader()) { c.st->niters = k; c.st->hist_len = hlen; c.st->solved = cgresidNorm <= stopTol; }
+}
+
+// ---------------------------------------------------------------------------
+// Arnoldi helpers for cpgmres / cpdqgmres.  The reference's Gram-Schmidt
+// coefficients use the FIXED u, t (cpgmres.m:215, cpdqgmres.m:213), so all of
+// them come out of one pass over the basis; the subtraction then runs in the
+// reference's j order.
+//   cols[j] (j < nc) = column index into the basis VQ for the j-th coefficient
+//   hs (shared)      = coefficients out
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void multi_dot(Ctx<Team> &c, const double *VQ, const int *cols, int nc, const double *U, double *hs)
+{
+    Team &T = c.T;
+    const int N = c.N;
+    for (int j0 = 0; j0 < nc; j0 += kRedMax) {
+        const int nv = min(kRedMax, nc - j0);
+        double acc[kRedMax];
+        const double *colp[kRedMax];
+#pragma unroll
+        for (int j = 0; j < kRedMax; ++j) { acc[j] = 0.0; colp[j] = VQ + (size_t)cols[j0 + min(j, nv - 1)] * N; }
+        TEAM_FOR(T, i, N) {
+            const double u = U[i];
+#pragma unroll
+            for (int j = 0; j < kRedMax; ++j) acc[j] += colp[j][i] * u;
+        }
+        T.template wide_store<kRedMax>(acc, j0, nv, hs);
+    }
+    T.wide_collect(nc, hs);
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpgmres.m:130-269
+// work: 0 U 1 W 2.. basis VQ (restart+1 columns)
+// dynamic shared (doubles): hs[r+1] cs[r] sn[r] g[r+1] z[r] ; cols (int) after
+// global scratch gs: H (r+1) x r column-major (team leader only)
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    const int R = c.A.restart;
+    double *U = c.vec(0), *W = c.vec(1), *VQ = c.vec(2);
+    double *hs = c.dsm, *csn = hs + (R + 1), *snn = csn + R, *g = snn + R, *z = g + (R + 1);
+    int *cols = (int *)(z + R);
+    double *Hg = c.A.gs;                        // (R+1) x R
+    __shared__ double s_resid;
+    __shared__ int s_err;
+
+    TEAM_FOR(T, i, N) X[i] = 0.0;
+    for (int j = threadIdx.x; j <= R; j += blockDim.x) cols[j] = j;
+    bool finished = false;
+    long long outer = 0;
+    const long long outermax = (c.A.itmax + R - 1) / R;             // :148
+    double residNorm = 0.0, stopTol = 0.0;
+    long long hl = 0;
+    int k = 0;
+    T.sync();
+    while (!finished && outer < outermax) {                         // :155
+        ++outer;
+        double part[1] = {0.0};
+        if (outer == 1) {                                           // :160-165
+            TEAM_FOR(T, i, N) U[i] = (i < n) ? b[i] : 0.0;
+            T.sync();
+        } else {                                                    // :166-168
+            c.pc.mark(CPK_PH_VEC_);
+            spmv_sell(T, c.S.HC, X, [&](int row, double s) { U[row] = (row < n) ? b[row] - s : s; });
+            T.sync();
+            c.pc.mark(CPK_PH_SPMV_);
+        }
+        c.apply(U, true, W);
+        double *V1 = VQ;
+        TEAM_FOR(T, i, N) {
+            double v;
+            if (i < n) v = W[i];
+            else v = (outer == 1) ? -W[i] : X[i] - W[i];            // :165 / :171
+            V1[i] = v;
+            part[0] += U[i] * v;
+        }
+        T.template reduce<1>(part);
+        if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)((outer - 1) * R), part[0]); return; }
+        residNorm = sqrt(part[0]);                                  // :173
+        if (residNorm != 0.0) { TEAM_FOR(T, i, N) V1[i] = V1[i] / residNorm; }
+        if (outer == 1) { stopTol = c.A.atol + c.A.rtol * residNorm; c.hist(0, 0, residNorm); hl = 1; }
+        k = 0;
+        if (T.cta_leader()) g[0] = residNorm;
+        T.sync();
+        while (residNorm > stopTol && k < R) {                      // :203
+            ++k;
+            const double *Vk = VQ + (size_t)(k - 1) * N;
+            double *Vk1 = VQ + (size_t)k * N;
+            c.pc.mark(CPK_PH_VEC_);
+            spmv_sell(T, c.S.HC, Vk, [&](int row, double s) { U[row] = s; });   // :209-210
+            T.sync();
+            c.pc.mark(CPK_PH_SPMV_);
+            c.apply(U, true, W);                                    // :211
+            multi_dot(c, VQ, cols, k, U, hs);                       // :215
+            part[0] = 0.0;
+            TEAM_FOR(T, i, N) {                                     // :212-218
+                double v = (i < n) ? W[i] : Vk[i] - W[i];
+                for (int j = 0; j < k; ++j) v = v - hs[j] * VQ[(size_t)j * N + i];
+                Vk1[i] = v;
+                part[0] += U[i] * v;
+            }
+            T.template reduce<1>(part);
+            if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)((outer - 1) * R + k), part[0]); return; }
+            const double hk1 = sqrt(part[0]);                       // :219
+            if (hk1 != 0.0) { TEAM_FOR(T, i, N) Vk1[i] = Vk1[i] / hk1; }
+            // scalar part, one thread per CTA, identical in every CTA (:229-248)
+            if (T.cta_leader()) {
+                for (int j = 0; j < k - 1; ++j) {
+                    const double Hjk = csn[j] * hs[j] + snn[j] * hs[j + 1];
+                    hs[j + 1] = snn[j] * hs[j] - csn[j] * hs[j + 1];
+                    hs[j] = Hjk;
+                }
+                double cc, ss, dd;
+                sym_givens(hs[k - 1], hk1, cc, ss, dd);
+                csn[k - 1] = cc; snn[k - 1] = ss; hs[k - 1] = dd;
+                g[k] = ss * g[k - 1];
+                g[k - 1] = cc * g[k - 1];
+                s_resid = fabs(g[k]);
+                if (T.leader()) for (int j = 0; j < k; ++j) Hg[(size_t)(k - 1) * (R + 1) + j] = hs[j];
+            }
+            T.sync();
+            residNorm = s_resid;
+            c.hist(0, hl, residNorm); ++hl;
+            c.pc.mark(CPK_PH_VEC_);
+        }
+        // z = H(1:k,1:k) \ g(1:k) by the team leader's warp (:257), then x += V z, y -= Q z
+        if (T.gwarp == 0) {
+            for (int i = k - 1; i >= 0; --i) {
+                double acc = 0.0;
+                for (int j = i + 1 + T.lane; j < k; j += 32) acc += Hg[(size_t)j * (R + 1) + i] * z[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                if (T.lane == 0) {
+                    const double zi = (g[i] - acc) / Hg[(size_t)i * (R + 1) + i];
+                    z[i] = zi;
+                    c.A.gs[(size_t)(R + 1) * R + i] = zi;
+                }
+                __syncwarp();
+            }
+        }
+        T.sync();
+        for (int j = threadIdx.x; j < k; j += blockDim.x) z[j] = ld_cg(&c.A.gs[(size_t)(R + 1) * R + j]);
+        T.cta_sync();
+        TEAM_FOR(T, i, N) {                                         // :258-260
+            double acc = 0.0;
+            for (int j = 0; j < k; ++j) acc += VQ[(size_t)j * N + i] * z[j];
+            X[i] = (i < n) ? X[i] + acc : X[i] - acc;
+        }
+        finished = residNorm <= stopTol;
+        T.sync();
+        c.pc.mark(CPK_PH_VEC_);
+    }
+    (void)s_err;
+    if (T.leader()) {
+        c.st->niters = (outer > 0 ? (outer - 1) * R : 0) + k;       // :267
+        c.st->hist_len = hl;
+        c.st->solved = residNorm <= stopTol;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernels/cpdqgmres.m:125-280
+// work: 0 U 1 W 2.. VQ ring (mem+1 columns), then PVQ ring (mem+1 columns)
+// dynamic shared (doubles): hs[mem+1] cs[mem] sn[mem] g[mem+1] pc[mem+1]
+//                           Hb[(mem+2) x (mem+3)]  band ring of H ; cols (int)
+// The reference's H(j, 2+k-j) (itmax x (mem+2), cpdqgmres.m:133) is kept as a
+// ring over the live rows j mod (mem+2).
+// ---------------------------------------------------------------------------
+template <class Team>
+__device__ void run_cpdqgmres(Ctx<Team> &c, const double *b, double *X)
+{
+    Team &T = c.T;
+    const int n = c.n, N = c.N;
+    const int mem = c.A.mem;
+    const int M1 = mem + 1, HR = mem + 2, HC_ = mem + 3;
+    double *U = c.vec(0), *W = c.vec(1), *VQ = c.vec(2), *PVQ = c.vec(2 + M1);
+    double *hs = c.dsm, *csn = hs + M1, *snn = csn + mem, *g = snn + mem, *pcf = g + M1, *Hb = pcf + M1;
+    int *cols = (int *)(Hb + (size_t)HR * HC_);
+    __shared__ double s_scal[4];        // residNorm, H(k,2), g(kpos)
+
+#define HB(j, kk) Hb[(size_t)((j) % HR) * HC_ + (kk)]
+    for (int j = threadIdx.x; j < HR * HC_; j += blockDim.x) Hb[j] = 0.0;
+    TEAM_FOR(T, i, N) { X[i] = 0.0; U[i] = (i < n) ? b[i] : 0.0; }
+    T.sync();
+    c.apply(U, false, W);                                           // :151
+    double part[1] = {0.0};
+    TEAM_FOR(T, i, N) {
+        const double v = (i < n) ? W[i] : -W[i];
+        VQ[i] = v;
+        if (i < n) part[0] += U[i] * v;
+    }
+    T.template reduce<1>(part);
+    if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, 0, part[0]); return; }
+    double residNorm = sqrt(part[0]);                               // :154
+    if (residNorm != 0.0) { TEAM_FOR(T, i, N) VQ[i] = VQ[i] / residNorm; }
+    long long k = 0;
+    if (T.cta_leader()) g[0] = residNorm;
+    const double stopTol = c.A.atol + c.A.rtol * residNorm;
+    c.hist(0, 0, residNorm);
+    T.sync();
+    while (residNorm > stopTol && k < c.A.itmax) {                  // :194
+        ++k;
+        const int kpos = (int)((k - 1) % M1);                       // 0-based slots (:199-201)
+        const int kp1pos = (int)(k % M1);
+        const int rotpos = (int)((k - 1) % mem);
+        const double *Vk = VQ + (size_t)kpos * N;
+        double *Vk1 = VQ + (size_t)kp1pos * N;
+        c.pc.mark(CPK_PH_VEC_);
+        spmv_sell(T, c.S.HC, Vk, [&](int row, double s) { U[row] = s; });       // :205-206
+        T.sync();
+        c.pc.mark(CPK_PH_SPMV_);
+        c.apply(U, true, W);                                        // :207
+        const long long jlo = (k - mem + 1 > 1) ? k - mem + 1 : 1;  // :210
+        const int nc = (int)(k - jlo + 1);
+        T.cta_sync();
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) cols[j] = (int)((jlo + j - 1) % M1);
+        T.cta_sync();
+        multi_dot(c, VQ, cols, nc, U, hs);                          // :213
+        part[0] = 0.0;
+        TEAM_FOR(T, i, N) {                                         // :208-216
+            double v = (i < n) ? W[i] : Vk[i] - W[i];
+            for (int j = 0; j < nc; ++j) v = v - hs[j] * VQ[(size_t)cols[j] * N + i];
+            Vk1[i] = v;
+            part[0] += U[i] * v;
+        }
+        T.template reduce<1>(part);
+        if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)k, part[0]); return; }
+        const double hk1 = sqrt(part[0]);                           // :218
+        const long long plo = (k - mem > 1) ? k - mem : 1;          // :228, :255
+        const int np = (int)(k - plo);
+        if (T.cta_leader()) {
+            for (int j = 0; j < nc; ++j) HB(jlo + j, 2 + k - (jlo + j)) = hs[j];
+            HB(k, 1) = hk1;
+            for (long long j = plo; j <= k - 1; ++j) {              // :228-235
+                const int jr = (int)((j - 1) % mem);
+                const int kk = (int)(k - j + 1), kk1 = kk + 1;
+                const double a = HB(j, kk1), bb = HB(j + 1, kk);
+                const double Hjk = csn[jr] * a + snn[jr] * bb;
+                HB(j + 1, kk) = snn[jr] * a - csn[jr] * bb;
+                HB(j, kk1) = Hjk;
+            }
+            double cc, ss, dd;
+            sym_givens(HB(k, 2), HB(k, 1), cc, ss, dd);             // :243
+            csn[rotpos] = cc; snn[rotpos] = ss;
+            HB(k, 2) = dd; HB(k, 1) = 0.0;
+            g[kp1pos] = ss * g[kpos];
+            g[kpos] = cc * g[kpos];
+            for (int j = 0; j < np; ++j) pcf[j] = HB(plo + j, 2 + k - (plo + j));
+            s_scal[0] = fabs(g[kp1pos]);
+            s_scal[1] = dd;
+            s_scal[2] = g[kpos];
+            // the row that leaves the band must read as zero when its slot is reused
+            for (int kk = 0; kk < HC_; ++kk) HB(k + 2, kk) = 0.0;
+        }
+        T.cta_sync();
+        for (int j = threadIdx.x; j < np; j += blockDim.x) cols[j] = (int)((plo + j - 1) % M1);
+        T.cta_sync();
+        const double hk2 = s_scal[1], gk = s_scal[2];
+        double *PVk = PVQ + (size_t)kpos * N;
+        TEAM_FOR(T, i, N) {
+            if (hk1 != 0.0) Vk1[i] = Vk1[i] / hk1;                  // :222-225
+            double p = Vk[i];                                       // :253-263
+            for (int j = 0; j < np; ++j) p = p - pcf[j] * PVQ[(size_t)cols[j] * N + i];
+            p = p / hk2;
+            PVk[i] = p;
+            X[i] = (i < n) ? X[i] + gk * p : X[i] - gk * p;         // :264-265
+        }
+        residNorm = s_scal[0];                                      // :268
+        c.hist(0, k, residNorm);
+        T.sync();
+        c.pc.mark(CPK_PH_VEC_);
+    }
+#undef HB
+    if (T.leader()) { c.st->niters = k; c.st->hist_len = k + 1; c.st->solved = residNorm <= stopTol; }
+}
+
+// ---------------------------------------------------------------------------
+// Entry shared by all launches: optional reg_cpkrylov shift, solver dispatch,
+// un-shift (reg_cpkrylov.m:153-173).  X = A.x receives [x; y].
+// work vectors N..: the solvers use c.vec(i) above the two reserved here.
+// ---------------------------------------------------------------------------
+template <int SOLVER, class Team>
+__device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, double *dsm)
+{
+    SolveArgs A = A0;
+    Ctx<Team> c{T, S, A, A.status, PhaseClock(), 0, dsm, S.n, S.m, S.N};
+    c.epoch = *S.M.epoch;       // flags of earlier launches carry earlier epochs
+    const int n = S.n, N = S.N;
+    c.pc.start(A.profile && T.leader(), A.status->phase_cycles);
+    // two reserved N-vectors at the end of the workspace: XY0 and B1
+    double *XY0 = A.work + A.work_len - (size_t)2 * N;
+    double *B1 = XY0 + N;
+    const double *b1 = A.b;
+    bool shift = false;
+    if (A.reg_mode) {
+        double cnt[1] = {0.0};
+        TEAM_FOR(T, i, N) if (i >= n && A.b[i] != 0.0) cnt[0] += 1.0;       // any(b(n+1:n+m)), :154
+        T.template reduce<1>(cnt);
+        shift = cnt[0] > 0.0;
+        if (shift) {
+            TEAM_FOR(T, i, N) B1[i] = (i < n) ? 0.0 : A.b[i];
+            T.sync();
+            VecIn in{B1, nullptr, n, false};
+            ldl2_apply(T, S.M, in, XY0, c.epoch, c.st, c.pc);              // :156
+            // b1 = b(1:n) - A*xy0(1:n) - B'*xy0(n+1:n+m)                    :157
+            spmv_sell(T, S.Hn, XY0, [&](int row, double s) { B1[row] = A.b[row] - s; });
+            T.sync();
+            spmv_sell(T, S.M.K12, XY0 + n, [&](int row, double s) { B1[row] = B1[row] - s; });
+            T.sync();
+            b1 = B1;
+        }
+        if (T.leader()) A.status->shifted = shift;
+        c.pc.mark(CPK_PH_OTHER_);
+    }
+    double *X = A.x;
+    if (SOLVER == 0) run_cpcg(c, b1, X);
+    else if (SOLVER == 1) run_cpcglanczos(c, b1, X);
+    else if (SOLVER == 2) run_cpminres(c, b1, X);
+    else if (SOLVER == 3) run_cpsymmlq(c, b1, X);
+    else if (SOLVER == 4) run_cpgmres(c, b1, X);
+    else if (SOLVER == 5) run_cpdqgmres(c, b1, X);
+    c.pc.mark(CPK_PH_VEC_);
+    if (shift) {                                                            // :166-168
+        TEAM_FOR(T, i, N) X[i] = XY0[i] + X[i];
+    }
+    T.sync();
+    c.pc.mark(CPK_PH_OTHER_);
+    if (T.leader()) {
+        *S.M.epoch = c.epoch;
+        if (T.aborted()) A.status->err = CPK_ERR_TIMEOUT_;
+    }
+}
+
+// One persistent kernel per (solver, team kind).  GRID: cooperative launch, the
+// whole grid works on sys[0]; otherwise CTA b works on sys[b] (batch).
+extern __shared__ double g_dsm[];
+
+template <int SOLVER, bool GRID>
+__global__ void __launch_bounds__(kBlock, 1)
+k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols)
+{
+    __shared__ TeamShared sh;
+    if (GRID) {
+        GridTeam T;
+        T.init(ctl, partials, &sh);
+        T.wide = wide; T.wide_cols = wide_cols;
+        solve_entry<SOLVER>(T, sys[0], args[0], g_dsm);
+    } else {
+        CtaTeam T;
+        T.init(ctl + blockIdx.x, nullptr, &sh);
+        solve_entry<SOLVER>(T, sys[blockIdx.x], args[blockIdx.x], g_dsm);
+    }
+}
+
+}  // namespace cpk
+
+// Each solver is compiled in its own translation unit (cpk_solve_<name>.cu):
+//   CPK_DEFINE_SOLVER_TU(id, name) exports  const void *cpk_kernel_<name>(int grid)
+#define CPK_DEFINE_SOLVER_TU(ID, NAME)                                                     \
+    extern "C" const void *cpk_kernel_##NAME(int grid)                                     \
+    {                                                                                      \
+        return grid ? (const void *)cpk::k_solve<ID, true> : (const void *)cpk::k_solve<ID, false>; \
+    }
