@@ -37,6 +37,14 @@ struct DevSell {
     const double *lval;
 };
 
+// A value and the tag (solve epoch) that says it is ready.  16-byte aligned so
+// that ld/st.relaxed.gpu.b128 moves both in one single-copy-atomic access: no
+// fence is needed between "data" and "flag" because they are the same word.
+struct __align__(16) Tagged {
+    double v;
+    unsigned long long tag;
+};
+
 // One triangular sweep of the LDL' solve in "item" form: an item is a SELL
 // slice of <=32 rows of the same dependency level, processed by one warp.
 // Column indices address the dependency buffer directly (LDL row ids).
@@ -57,9 +65,9 @@ struct DevLdl {
     const int    *b_partner;// LDL row id of the 2x2 partner or -1
     const double *b_e;      // off-diagonal of the 2x2 block (valid if partner>=0)
     const double *b_dp;     // partner's diagonal entry
-    // sync-free state (row-id indexed)
-    double *wbuf, *ybuf;
-    int    *wflag, *yflag;
+    // sync-free state (row-id indexed): value + the epoch of the solve that
+    // produced it, read and written as ONE 128-bit atomic access
+    Tagged *wbuf, *ybuf;
     int    *epoch;          // [1] device-resident solve counter
     // K_P = [A B'; B C] for the refinement residual and `divide`
     DevSell KP;
@@ -142,6 +150,20 @@ __device__ __forceinline__ double ld_cg(const double *p) {
 }
 __device__ __forceinline__ void st_cg(double *p, double v) {
     asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ Tagged ld_tagged(const Tagged *p) {
+    unsigned long long lo, hi;
+    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+                 : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    Tagged r;
+    r.v = __longlong_as_double((long long)lo);
+    r.tag = hi;
+    return r;
+}
+__device__ __forceinline__ void st_tagged(Tagged *p, double v, unsigned long long tag) {
+    const unsigned long long lo = (unsigned long long)__double_as_longlong(v);
+    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%0, %1};\n\tst.relaxed.gpu.global.b128 [%2], t;\n\t}"
+                 :: "l"(lo), "l"(tag), "l"(p) : "memory");
 }
 __device__ __forceinline__ int ld_volatile(const int *p) {
     int v;

@@ -657,10 +657,8 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     CUDA_TRY(o->ar.upload(&m.b_partner, bpart));
     CUDA_TRY(o->ar.upload(&m.b_e, be));
     CUDA_TRY(o->ar.upload(&m.b_dp, bdp));
-    CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));
+    CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));        // tag 0 = never produced; epochs start at 1
     CUDA_TRY(o->ar.alloc(&m.ybuf, N, true));
-    CUDA_TRY(o->ar.alloc(&m.wflag, N, true));
-    CUDA_TRY(o->ar.alloc(&m.yflag, N, true));
     CUDA_TRY(o->ar.alloc(&m.epoch, 1, true));
     CUDA_TRY(upload_sell(o->ar, sKP, m.KP));
     CUDA_TRY(upload_sell(o->ar, sK12, m.K12));

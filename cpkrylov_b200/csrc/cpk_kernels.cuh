@@ -94,8 +94,9 @@ struct VecIn {
 // Ends WITHOUT a team barrier: the caller syncs before `out` is gathered.
 // ---------------------------------------------------------------------------
 template <class Team>
-__device__ __noinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn &in, double *out, bool accumulate, int epoch)
+__device__ __noinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn &in, double *out, bool accumulate, int epoch_i)
 {
+    const unsigned long long epoch = (unsigned long long)(unsigned)epoch_i;
     const int nf = M.fwd.nitems, nb = M.bwd.nitems;
     for (int it = T.gwarp; it < nf + nb; it += T.nwarps) {
         const bool fwd = it < nf;
@@ -109,12 +110,13 @@ __device__ __noinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn &in
         int k = beg + T.lane;
         double acc = 0.0;
         int stage = 0;          // backward rows: 0 = still waiting for own (and partner) w
-        int pidx = 0;
-        const double *dep; const int *depflag;
-        if (fwd) { dep = M.wbuf; depflag = M.wflag; } else { dep = M.ybuf; depflag = M.yflag; }
+        int pidx = 0, partner = -1;
+        double dd = 1.0;
+        const Tagged *dep = fwd ? M.wbuf : M.ybuf;
         if (!done) {
             pidx = __ldg(&S.pidx[slot]);
             if (fwd) { acc = in(pidx); stage = 1; }
+            else { partner = __ldg(&M.b_partner[slot]); dd = __ldg(&M.b_d[slot]); }
         }
         long long t0 = clock64();
         unsigned spins = 0;
@@ -122,39 +124,46 @@ __device__ __noinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn &in
             if (!done) {
                 if (stage == 0) {
                     // D-solve on entry of the backward row (opLDL2.m:86, inv(op.D))
-                    const int partner = __ldg(&M.b_partner[slot]);
-                    bool ready = ld_acquire(&M.wflag[rid]) == epoch;
-                    if (ready && partner >= 0) ready = ld_acquire(&M.wflag[partner]) == epoch;
-                    if (ready) {
-                        const double w = ld_cg(&M.wbuf[rid]);
-                        const double d = __ldg(&M.b_d[slot]);
-                        if (partner < 0) {
-                            acc = w / d;
-                        } else {
+                    const Tagged w = ld_tagged(&M.wbuf[rid]);
+                    if (partner < 0) {
+                        if (w.tag == epoch) { acc = w.v / dd; stage = 1; }
+                    } else {
+                        const Tagged wp = ld_tagged(&M.wbuf[partner]);
+                        if (w.tag == epoch && wp.tag == epoch) {
                             const double e = __ldg(&M.b_e[slot]);
                             const double dp = __ldg(&M.b_dp[slot]);
-                            const double wp = ld_cg(&M.wbuf[partner]);
-                            const double det = d * dp - e * e;
-                            acc = (dp * w - e * wp) / det;
+                            const double det = dd * dp - e * e;
+                            acc = (dp * w.v - e * wp.v) / det;
+                            stage = 1;
                         }
-                        stage = 1;
                     }
                 }
                 if (stage == 1) {
+                    // up to 4 dependencies in flight; consumed strictly in row order
                     while (k < end) {
-                        const int c = __ldg(&S.col[k]);
-                        if (c < 0) { k = end; break; }
-                        if (ld_acquire(&depflag[c]) != epoch) break;
-                        acc -= __ldg(&S.val[k]) * ld_cg(&dep[c]);
-                        k += 32;
+                        int c[4]; double v[4]; Tagged t[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) c[u] = (k + 32 * u < end) ? __ldg(&S.col[k + 32 * u]) : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (c[u] >= 0) { v[u] = __ldg(&S.val[k + 32 * u]); t[u] = ld_tagged(&dep[c[u]]); }
+                            else { v[u] = 0.0; t[u].v = 0.0; t[u].tag = epoch; }
+                        }
+                        bool stalled = false;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (stalled) continue;
+                            if (c[u] < 0) { k = end; stalled = true; }
+                            else if (t[u].tag == epoch) { acc -= v[u] * t[u].v; k += 32; }
+                            else stalled = true;
+                        }
+                        if (stalled) break;
                     }
                     if (k >= end) {
                         if (fwd) {
-                            st_cg(&M.wbuf[rid], acc);
-                            st_release(&M.wflag[rid], epoch);
+                            st_tagged(&M.wbuf[rid], acc, epoch);
                         } else {
-                            st_cg(&M.ybuf[rid], acc);
-                            st_release(&M.yflag[rid], epoch);
+                            st_tagged(&M.ybuf[rid], acc, epoch);
                             if (accumulate) out[pidx] = out[pidx] + acc; else out[pidx] = acc;
                         }
                         done = true;
