@@ -7,7 +7,7 @@
 
 namespace cpk {
 
-constexpr int kBlock      = 1024;   // threads per CTA: 1 CTA per SM, <=64 regs/thread
+constexpr int kBlock      = 512;    // threads per CTA: 1 CTA per SM, <=128 regs/thread (no spills in the streaming loops)
 constexpr int kWarpsPerCta = kBlock / 32;
 constexpr int kRedMax     = 8;      // values reduced together in one team reduction
 constexpr unsigned FULL   = 0xffffffffu;
@@ -30,6 +30,10 @@ struct DevSell {
     const int    *col;      // padded entries: val = 0, col = a valid column of that row (or 0)
     const double *val;
     const int    *rowmap;   // [nslices*32] output row of each lane, -1 = no row
+    // contiguous slice range of every warp, balanced by padded entries, for the
+    // two team shapes (0: cooperative grid, 1: one CTA): [nws[k]+1] each
+    const int    *wsplit[2];
+    int nws[2];
     int nlong;              // rows handled warp-per-row
     const int    *lrow;     // [nlong] row index
     const int    *lptr;     // [nlong+1]
@@ -45,30 +49,48 @@ struct __align__(16) Tagged {
     unsigned long long tag;
 };
 
-// One triangular sweep of the LDL' solve in "item" form: an item is a SELL
-// slice of <=32 rows of the same dependency level, processed by one warp.
-// Column indices address the dependency buffer directly (LDL row ids).
+// The LDL' solve as ONE ordered list of "items".  An item is a SELL slice of
+// <= 32 rows of the same dependency level, processed by one warp; forward items
+// (rows of L) come first, backward items (rows of L', D-solve fused in) follow.
+// Rows that need no work are compiled away at setup:
+//   * a row of L with no off-diagonal entry has w_i = (P'z)_i: it gets NO forward
+//     item, and whoever needs w_i reads the input vector directly (col <= -2);
+//   * a row whose column of L is empty has y_i = w_i/d_i: finished inside its
+//     forward item (F_FUSED), it gets NO backward item.
+// Column indices >= 0 address the tagged buffer of the sweep (LDL row ids),
+// -1 is padding, c <= -2 means input element -c-2.
+constexpr int F_FWD = 1, F_FUSED = 2, F_STORE = 4, F_WDIRECT = 8, F_PARTNER = 16;
+// F_WARPROW (lane 0 of an item): the item is ONE long row, its entries spread over the 32 lanes
+constexpr int F_WARPROW = 32;
+
 struct DevSweep {
-    int nitems;
+    int nitems, nfwd;
+    int nseg;
+    const int    *seg;      // [3*nseg] (first item, end item, items per warp block): sync-free walk
+    int nlev;
+    const int    *levptr;   // [nlev+1] first item of every dependency level: level-synchronous walk
     const int    *sptr;     // [nitems+1]
-    const int    *col;      // -1 = padding
+    const int    *col;
     const double *val;
     const int    *rid;      // [nitems*32] LDL row id, -1 = idle lane
     const int    *pidx;     // [nitems*32] index into the user vector (perm[rid])
+    const int    *flags;    // [nitems*32] F_* bits
+    const double *d;        // [nitems*32] own diagonal entry of D
+    const int    *partner;  // [nitems*32] 2x2 partner row id (F_PARTNER)
+    const double *e;        // off-diagonal of the 2x2 block
+    const double *dp;       // partner's diagonal entry
 };
 
 struct DevLdl {
     int N, nA, nC;
-    DevSweep fwd, bwd;
-    // D-solve data, indexed like bwd.rid (per lane of the backward sweep)
-    const double *b_d;      // own diagonal entry
-    const int    *b_partner;// LDL row id of the 2x2 partner or -1
-    const double *b_e;      // off-diagonal of the 2x2 block (valid if partner>=0)
-    const double *b_dp;     // partner's diagonal entry
+    DevSweep sw;
     // sync-free state (row-id indexed): value + the epoch of the solve that
     // produced it, read and written as ONE 128-bit atomic access
     Tagged *wbuf, *ybuf;
     int    *epoch;          // [1] device-resident solve counter
+    // level-synchronous state: plain values, a team barrier separates the levels
+    double *wv, *yv;
+    int    sync_free;       // 1: tagged sync-free walk, 0: one barrier per level
     // K_P = [A B'; B C] for the refinement residual and `divide`
     DevSell KP;
     DevSell K12, K22;       // B' (nA x nC) and C (nC x nC) for the stateful residual update
@@ -121,6 +143,8 @@ struct SolveArgs {
     long long hist_cap;
     double *gs;             // GMRES/DQGMRES scalar scratch in global memory
     DevStatus *status;
+    int     ring_off;       // byte offset of the per-warp bulk-copy rings in dynamic shared memory
+    int     ring_elems;     // entries per ring stage (0: rings disabled)
 };
 
 // ---------------------------------------------------------------------------
@@ -186,20 +210,73 @@ constexpr long long kWatchdogCycles = 4000000000LL;   // ~2 s of SM clocks
 //   CtaTeam : a single CTA (small systems; a batch launch runs many of them)
 // Both expose: tid/nthreads, gwarp/nwarps/lane, sync(), reduce<K>().
 // ---------------------------------------------------------------------------
+constexpr int kRingStages = 4;      // bulk-copy stages in flight per warp
+
 struct TeamShared {
     double red[kWarpsPerCta][kRedMax];
     double out[kRedMax];
+    unsigned long long ringbar[kWarpsPerCta][kRingStages];     // mbarriers of the per-warp rings
+};
+
+// ---------------------------------------------------------------------------
+// Per-warp shared-memory ring fed by the bulk-copy (TMA) engine.  A warp streams
+// a contiguous span of a matrix (val[], col[]) through kRingStages stages of
+// `elems` entries: lane 0 posts cp.async.bulk copies that complete on the
+// stage's mbarrier, the 32 lanes wait on it and read their entries from shared
+// memory.  The copies in flight (stages x 12 B x elems per warp) are what covers
+// the HBM latency; no registers and no other warp are involved.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+struct WarpRing {
+    char *base;                 // this warp's stages (shared memory), nullptr = ring disabled
+    unsigned long long *bar;    // this warp's kRingStages mbarriers
+    int elems;                  // entries per stage, multiple of 32
+    unsigned n;                 // stage uses so far (selects stage and mbarrier phase)
+
+    __device__ void init(char *dsm_ring, int elems_, TeamShared *sh) {
+        const int w = threadIdx.x >> 5;
+        elems = elems_;
+        n = 0;
+        bar = sh ? sh->ringbar[w] : nullptr;
+        base = (dsm_ring && elems_ > 0 && sh) ? dsm_ring + (size_t)w * kRingStages * 12 * elems_ : nullptr;
+        if (base && (threadIdx.x & 31) == 0)
+            for (int i = 0; i < kRingStages; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+    __device__ __forceinline__ double *val(int st) const { return reinterpret_cast<double *>(base + (size_t)st * 12 * elems); }
+    __device__ __forceinline__ int *col(int st) const { return reinterpret_cast<int *>(base + (size_t)st * 12 * elems + (size_t)8 * elems); }
 };
 
 struct GridTeam {
+    static constexpr int kKind = 0;
     int tid, nthreads, gwarp, nwarps, lane;
     TeamCtl *ctl;
     double  *partials;      // [2][kRedMax][gridDim.x]
     TeamShared *sh;
     unsigned bar_target;
     unsigned red_parity;
+    WarpRing ring;
 
-    __device__ void init(TeamCtl *c, double *p, TeamShared *s) {
+    __device__ void init(TeamCtl *c, double *p, TeamShared *s, char *dsm_ring = nullptr, int ring_elems = 0) {
+        ring.init(dsm_ring, ring_elems, s);
         tid = blockIdx.x * blockDim.x + threadIdx.x;
         nthreads = gridDim.x * blockDim.x;
         gwarp = tid >> 5;
@@ -250,7 +327,7 @@ struct GridTeam {
         if (w == 0) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                double s = sh->red[lane][k];
+                double s = (lane < kWarpsPerCta) ? sh->red[lane][k] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0)
@@ -294,7 +371,7 @@ struct GridTeam {
         if (w == 0) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                double s = sh->red[lane][k];
+                double s = (lane < kWarpsPerCta) ? sh->red[lane][k] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0 && k < nvalid)
@@ -319,11 +396,14 @@ struct GridTeam {
 };
 
 struct CtaTeam {
+    static constexpr int kKind = 1;
     int tid, nthreads, gwarp, nwarps, lane;
     TeamCtl *ctl;
     TeamShared *sh;
+    WarpRing ring;
 
-    __device__ void init(TeamCtl *c, double *, TeamShared *s) {
+    __device__ void init(TeamCtl *c, double *, TeamShared *s, char *dsm_ring = nullptr, int ring_elems = 0) {
+        ring.init(dsm_ring, ring_elems, s);
         tid = threadIdx.x;
         nthreads = blockDim.x;
         gwarp = tid >> 5;

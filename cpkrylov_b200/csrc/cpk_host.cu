@@ -207,55 +207,186 @@ static HSell build_sell(const HCsr &A)
 }
 
 // ---------------------------------------------------------------------------
-// Triangular sweep builder: rows grouped by dependency level, sorted by length
-// inside a level, cut into slices (items) that never straddle a level.
-// deps: CSR of the STRICT triangle in LDL index space.
+// LDL' sweep builder.  Produces the unified item list of DevSweep: forward items
+// (level order), then backward items (level order), with the rows that need no
+// work compiled away (see cpk_device.cuh) and the segment table that tells the
+// kernel how to deal items to warps (blocks of consecutive items for bulk
+// levels, one item per warp for chains).
 // ---------------------------------------------------------------------------
 struct HSweep {
-    int nitems = 0, nlevels = 0;
-    std::vector<int> sptr, col, rid, pidx;
-    std::vector<double> val;
+    int nitems = 0, nfwd = 0;
+    std::vector<int> seg, levptr, sptr, col, rid, pidx, flags, partner;
+    std::vector<double> val, d, e, dp;
+    int64_t n_trivial = 0, n_fused = 0, tail_f = 0, tail_b = 0, n_warprow = 0, max_len = 0;
+    int lev_f_eff = 0, lev_b_eff = 0;
 };
 
-static HSweep build_sweep(const HCsr &deps, const std::vector<int> &level, int nlevels, const std::vector<int64_t> &perm)
+struct SweepRow { int row; int level; int len; };
+constexpr int kLongRow = 8;         // rows with more entries are walked by a whole warp
+typedef std::vector<std::pair<int, double>> EncRow;     // (column code, value), in accumulation order
+
+// Appends the rows (already filtered) of one direction.  `entries(r)` returns the
+// encoded dependency list of LDL row r.
+// Items of a level are created sorted by cost (long rows first).  Deal them
+// round-robin to the `nw` warps that will walk the level and store every
+// warp's hand contiguously: each warp still streams a contiguous range, and
+// every range holds the same mix of expensive and cheap items.
+static void deal_level(HSweep &W, int first, int n, int nw)
 {
-    HSweep W;
-    W.nlevels = nlevels;
-    const int N = deps.nrows;
-    std::vector<int> order(N);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        if (level[a] != level[b]) return level[a] < level[b];
-        return deps.len(a) > deps.len(b);
-    });
-    W.sptr.push_back(0);
-    size_t i0 = 0;
-    while (i0 < (size_t)N) {
-        size_t i1 = i0;
-        const int lev = level[order[i0]];
-        while (i1 < (size_t)N && i1 - i0 < 32 && level[order[i1]] == lev) ++i1;
-        int width = 0;
-        for (size_t t = i0; t < i1; ++t) width = std::max(width, deps.len(order[t]));
-        const size_t base = W.col.size();
-        W.col.resize(base + (size_t)width * 32, -1);
-        W.val.resize(base + (size_t)width * 32, 0.0);
-        for (int lane = 0; lane < 32; ++lane) {
-            const size_t t = i0 + lane;
-            if (t < i1) {
-                const int r = order[t];
-                W.rid.push_back(r);
-                W.pidx.push_back((int)perm[r]);
-                for (int j = 0; j < deps.len(r); ++j) {
-                    W.col[base + (size_t)j * 32 + lane] = deps.col[deps.ptr[r] + j];
-                    W.val[base + (size_t)j * 32 + lane] = deps.val[deps.ptr[r] + j];
-                }
-            } else { W.rid.push_back(-1); W.pidx.push_back(0); }
-        }
-        W.sptr.push_back((int)W.col.size());
-        W.nitems++;
-        i0 = i1;
+    if (n <= 1 || nw <= 1) return;
+    std::vector<int> order;             // new position -> old item (relative)
+    order.reserve(n);
+    // warp w gets [n*w/nw, n*(w+1)/nw): fill these ranges by dealing
+    std::vector<std::vector<int>> hand(std::min(nw, n));
+    const int nh = (int)hand.size();
+    // ranges have sizes that differ by at most one; deal so that range sizes match
+    std::vector<int> cap(nh);
+    for (int w = 0; w < nh; ++w) cap[w] = (int)((long long)n * (w + 1) / nh) - (int)((long long)n * w / nh);
+    int w = 0;
+    for (int i = 0; i < n; ++i) {
+        int tries = 0;
+        while ((int)hand[w].size() >= cap[w] && tries < nh) { w = (w + 1) % nh; ++tries; }
+        hand[w].push_back(i);
+        w = (w + 1) % nh;
     }
-    return W;
+    for (auto &h : hand) for (int i : h) order.push_back(i);
+    // rebuild the item arrays of this level in the new order
+    const int s0 = W.sptr[first];
+    std::vector<int> col, sptr(1, s0), rid, pidx, flags, partner;
+    std::vector<double> val, d, e, dp;
+    for (int k = 0; k < n; ++k) {
+        const int it = first + order[k];
+        const int b = W.sptr[it], en = W.sptr[it + 1];
+        col.insert(col.end(), W.col.begin() + b, W.col.begin() + en);
+        val.insert(val.end(), W.val.begin() + b, W.val.begin() + en);
+        sptr.push_back(s0 + (int)col.size());
+        for (int l = 0; l < 32; ++l) {
+            const size_t sl = (size_t)it * 32 + l;
+            rid.push_back(W.rid[sl]); pidx.push_back(W.pidx[sl]); flags.push_back(W.flags[sl]); partner.push_back(W.partner[sl]);
+            d.push_back(W.d[sl]); e.push_back(W.e[sl]); dp.push_back(W.dp[sl]);
+        }
+    }
+    std::copy(col.begin(), col.end(), W.col.begin() + s0);
+    std::copy(val.begin(), val.end(), W.val.begin() + s0);
+    for (int k = 0; k <= n; ++k) W.sptr[first + k] = sptr[k];
+    const size_t base = (size_t)first * 32;
+    std::copy(rid.begin(), rid.end(), W.rid.begin() + base);
+    std::copy(pidx.begin(), pidx.end(), W.pidx.begin() + base);
+    std::copy(flags.begin(), flags.end(), W.flags.begin() + base);
+    std::copy(partner.begin(), partner.end(), W.partner.begin() + base);
+    std::copy(d.begin(), d.end(), W.d.begin() + base);
+    std::copy(e.begin(), e.end(), W.e.begin() + base);
+    std::copy(dp.begin(), dp.end(), W.dp.begin() + base);
+}
+
+template <class Entries, class Flags>
+static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vector<int64_t> &perm,
+                         const std::vector<double> &dd, const std::vector<double> &ee, const std::vector<int> &partner,
+                         int grid_warps, Entries entries, Flags flags_of)
+{
+    // the team shape that will walk this system: whole grid for large N, one CTA otherwise
+    const int deal_warps = (int)perm.size() > 24576 ? grid_warps : kWarpsPerCta;
+    // inside a level any order is valid: group rows of equal (short) length and
+    // order them by their index in the user vector, so that the P' gather and the
+    // P scatter of consecutive lanes touch consecutive addresses
+    for (auto &rw : rows) W.max_len = std::max<int64_t>(W.max_len, rw.len);
+    std::stable_sort(rows.begin(), rows.end(), [&](const SweepRow &a, const SweepRow &b) {
+        if (a.level != b.level) return a.level < b.level;
+        const int la = std::min(a.len, kLongRow + 1), lb = std::min(b.len, kLongRow + 1);
+        if (la != lb) return la > lb;
+        return perm[a.row] < perm[b.row];
+    });
+    if (W.sptr.empty()) W.sptr.push_back(0);
+    // items per level
+    std::vector<std::pair<int, int>> level_items;       // (first item, count) per level, in order
+    size_t i0 = 0;
+    while (i0 < rows.size()) {
+        const int lev = rows[i0].level;
+        const int first_item = W.nitems;
+        while (i0 < rows.size() && rows[i0].level == lev) {
+            if (rows[i0].len > kLongRow) {
+                // one long row = one item, entries spread over the 32 lanes
+                const int r = rows[i0].row;
+                const EncRow er = entries(r);
+                const size_t width = (er.size() + 31) / 32;
+                const size_t base = W.col.size();
+                W.col.resize(base + width * 32, -1);
+                W.val.resize(base + width * 32, 0.0);
+                for (size_t jx = 0; jx < er.size(); ++jx) { W.col[base + jx] = er[jx].first; W.val[base + jx] = er[jx].second; }
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (lane == 0) {
+                        W.rid.push_back(r); W.pidx.push_back((int)perm[r]); W.flags.push_back(flags_of(r) | F_WARPROW); W.d.push_back(dd[r]);
+                        if (partner[r] >= 0) { W.partner.push_back(partner[r]); W.e.push_back(ee[std::min(r, partner[r])]); W.dp.push_back(dd[partner[r]]); }
+                        else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
+                    } else {
+                        W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
+                        W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
+                    }
+                }
+                W.sptr.push_back((int)W.col.size());
+                W.nitems++; W.n_warprow++;
+                ++i0;
+                continue;
+            }
+            size_t i1 = i0;
+            while (i1 < rows.size() && i1 - i0 < 32 && rows[i1].level == lev && rows[i1].len <= kLongRow) ++i1;
+            int width = 0;
+            for (size_t t = i0; t < i1; ++t) width = std::max(width, rows[t].len);
+            const size_t base = W.col.size();
+            W.col.resize(base + (size_t)width * 32, -1);
+            W.val.resize(base + (size_t)width * 32, 0.0);
+            for (int lane = 0; lane < 32; ++lane) {
+                const size_t t = i0 + lane;
+                if (t < i1) {
+                    const int r = rows[t].row;
+                    W.rid.push_back(r);
+                    W.pidx.push_back((int)perm[r]);
+                    W.flags.push_back(flags_of(r));
+                    W.d.push_back(dd[r]);
+                    if (partner[r] >= 0) {
+                        W.partner.push_back(partner[r]);
+                        W.e.push_back(ee[std::min(r, partner[r])]);
+                        W.dp.push_back(dd[partner[r]]);
+                    } else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
+                    const EncRow er = entries(r);
+                    for (size_t jx = 0; jx < er.size(); ++jx) {
+                        W.col[base + jx * 32 + lane] = er[jx].first;
+                        W.val[base + jx * 32 + lane] = er[jx].second;
+                    }
+                } else {
+                    W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
+                    W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
+                }
+            }
+            W.sptr.push_back((int)W.col.size());
+            W.nitems++;
+            i0 = i1;
+        }
+        level_items.emplace_back(first_item, W.nitems - first_item);
+        W.levptr.push_back(first_item);
+        deal_level(W, first_item, W.nitems - first_item, deal_warps);
+    }
+    // segments: a level with at least 2 items per warp is "bulk" (blocks of
+    // consecutive items per warp, prefetch pipeline); runs of smaller levels
+    // are merged into one chain segment dealt round-robin.
+    int chain_first = -1, chain_end = -1;
+    auto flush_chain = [&]() {
+        if (chain_first >= 0) { W.seg.push_back(chain_first); W.seg.push_back(chain_end); W.seg.push_back(1); }
+        chain_first = -1;
+    };
+    static const double bulk_min = [] { const char *e = getenv("CPK_LDL_BULK_MIN"); return e ? atof(e) : 2.0; }();
+    static const int blk_max = [] { const char *e = getenv("CPK_LDL_BLK"); return e ? atoi(e) : 8; }();
+    for (auto &li : level_items) {
+        if (li.second >= bulk_min * grid_warps) {
+            flush_chain();
+            const int blk = std::max(1, std::min(blk_max, li.second / grid_warps));
+            W.seg.push_back(li.first); W.seg.push_back(li.first + li.second); W.seg.push_back(blk);
+        } else {
+            if (chain_first < 0) chain_first = li.first;
+            chain_end = li.first + li.second;
+        }
+    }
+    flush_chain();
 }
 
 // ===========================================================================
@@ -292,10 +423,36 @@ struct DevArena {
     }
 };
 
+// contiguous slice ranges per warp, balanced by padded entries (+ a per-slice cost)
+static std::vector<int> warp_split(const std::vector<int> &sptr, int nslices, int nwarps)
+{
+    std::vector<int> out(nwarps + 1, nslices);
+    out[0] = 0;
+    const long long total = (nslices > 0 ? (long long)sptr[nslices] : 0) + 64LL * nslices;
+    int s = 0;
+    for (int w = 1; w < nwarps; ++w) {
+        const long long target = total * w / nwarps;
+        while (s < nslices && (long long)sptr[s] + 64LL * s < target) ++s;
+        out[w] = s;
+    }
+    out[nwarps] = nslices;
+    return out;
+}
+
+static int g_grid_warps_hint = 148 * kWarpsPerCta;
+
 static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d)
 {
     cudaError_t e;
     d.nrows = h.nrows; d.ncols = h.ncols; d.nslices = h.nslices;
+    {
+        const int nw[2] = {g_grid_warps_hint, kWarpsPerCta};
+        for (int kdx = 0; kdx < 2; ++kdx) {
+            std::vector<int> sp = warp_split(h.sptr, h.nslices, nw[kdx]);
+            if ((e = ar.upload(&d.wsplit[kdx], sp)) != cudaSuccess) return e;
+            d.nws[kdx] = nw[kdx];
+        }
+    }
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
@@ -310,12 +467,24 @@ static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d)
 static cudaError_t upload_sweep(DevArena &ar, const HSweep &h, DevSweep &d)
 {
     cudaError_t e;
-    d.nitems = h.nitems;
+    d.nitems = h.nitems; d.nfwd = h.nfwd; d.nseg = (int)h.seg.size() / 3;
+    if ((e = ar.upload(&d.seg, h.seg)) != cudaSuccess) return e;
+    {
+        std::vector<int> lp = h.levptr;
+        lp.push_back(h.nitems);
+        d.nlev = (int)h.levptr.size();
+        if ((e = ar.upload(&d.levptr, lp)) != cudaSuccess) return e;
+    }
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.rid, h.rid)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.pidx, h.pidx)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.flags, h.flags)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.d, h.d)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.partner, h.partner)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.e, h.e)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.dp, h.dp)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -398,7 +567,7 @@ static const void *solver_kernel(int solver, bool grid)
 }
 template <bool GRID> __global__ void k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st,
                                              TeamCtl *ctl, double *partials);
-template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y);
+template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y, int ring_elems);
 
 static int get_device_ctx(int device, DeviceCtx **out)
 {
@@ -427,11 +596,14 @@ static int get_device_ctx(int device, DeviceCtx **out)
         for (int g = 0; g < 2; ++g) {
             const void *k = solver_kernel(sv, g);
             CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
     c->grid_blocks = c->num_sms;    // one CTA per SM
     if (const char *e = getenv("CPK_GRID_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= c->num_sms * per_sm) c->grid_blocks = v; }
+    g_grid_warps_hint = c->grid_blocks * kWarpsPerCta;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -490,10 +662,25 @@ __global__ void __launch_bounds__(kBlock, 1)
 k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl *ctl, double *partials)
 {
     __shared__ TeamShared sh;
+    __shared__ DevLdl s_M;
+    {
+        const int *src = reinterpret_cast<const int *>(&sys->M);
+        int *dst = reinterpret_cast<int *>(&s_M);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevLdl) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
     PhaseClock pc; pc.start(false, nullptr);
-    const DevLdl &M = sys->M;
+    const DevLdl &M = s_M;
     VecIn in{z, nullptr, M.nA, false};
     int epoch = *M.epoch;
+    if (GRID && M.track_rnorm == 2) {
+        // debug timing of the level walk: per-level work / barrier cycles of CTA 0
+        GridTeam T; T.init(ctl, partials, &sh);
+        PhaseClock dbg; dbg.start(T.leader(), st->phase_cycles);
+        ldl_solve_levels(T, M, in, y, false, &dbg);
+        T.sync();
+        return;
+    }
     if (GRID) {
         GridTeam T; T.init(ctl, partials, &sh);
         ldl2_apply(T, M, in, y, epoch, st, pc);
@@ -509,13 +696,17 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
 
 template <bool GRID>
 __global__ void __launch_bounds__(kBlock, 1)
-k_matvec(DevSell A, const double *x, double *y)
+k_matvec(DevSell A, const double *x, double *y, int ring_elems)
 {
+    __shared__ TeamShared sh;
+    __shared__ TeamCtl dummy;       // only the watchdog flag of a stand-alone launch
+    if (threadIdx.x == 0) { dummy.bar = 0; dummy.abort = 0; }
+    char *ring = ring_elems > 0 ? reinterpret_cast<char *>(g_dsm) : nullptr;
     if (GRID) {
-        GridTeam T; T.init(nullptr, nullptr, nullptr);
+        GridTeam T; T.init(&dummy, nullptr, &sh, ring, ring_elems);
         spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
     } else {
-        CtaTeam T; T.init(nullptr, nullptr, nullptr);
+        CtaTeam T; T.init(&dummy, nullptr, &sh, ring, ring_elems);
         spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
     }
 }
@@ -622,23 +813,170 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) lv = std::max(lv, lb[Lcols.col[k]] + 1);
         lb[i] = lv; nlb = std::max(nlb, lv + 1);
     }
-    HSweep Wf = build_sweep(Lrows, lf, nlf, p);
-    HSweep Wb = build_sweep(Lcols, lb, nlb, p);
-    if ((int64_t)Wf.col.size() >= INT32_MAX || (int64_t)Wb.col.size() >= INT32_MAX)
-        return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
-    // D data per backward lane
-    std::vector<double> bd(Wb.rid.size(), 1.0), be(Wb.rid.size(), 0.0), bdp(Wb.rid.size(), 1.0);
-    std::vector<int> bpart(Wb.rid.size(), -1);
-    for (size_t s = 0; s < Wb.rid.size(); ++s) {
-        const int r = Wb.rid[s];
-        if (r < 0) continue;
-        bd[s] = d[r];
-        if (partner[r] >= 0) {
-            bpart[s] = partner[r];
-            be[s] = e[std::min(r, partner[r])];
-            bdp[s] = d[partner[r]];
-        }
+    // ---- classify rows and build the unified item list
+    std::vector<char> hasR(N), hasC(N), triv(N), fused(N);
+    for (int i = 0; i < N; ++i) {
+        hasR[i] = Lrows.len(i) > 0; hasC[i] = Lcols.len(i) > 0;
+        triv[i] = !hasR[i] && partner[i] < 0;                   // w_i = (P'z)_i, no forward item
+        fused[i] = hasR[i] && !hasC[i] && partner[i] < 0;       // y_i = w_i/d_i inside the forward item
     }
+    if (getenv("CPK_LDL_NO_SHORTCUTS")) { std::fill(triv.begin(), triv.end(), 0); std::fill(fused.begin(), fused.end(), 0); }
+    HSweep W;
+    // Depth reduction: the last levels of a sweep hold few rows but cost one
+    // cross-SM hop each.  Rows of levels >= cut are rewritten by substituting
+    // their in-tail dependencies (an explicit inverse of the small unit-
+    // triangular tail block, built row by row), so the whole tail becomes ONE
+    // level that depends only on earlier levels and on the input vector.
+    // Skipped when the substitution would fill in or grow too much.
+    static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 262144LL; }();
+    static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
+    static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
+    auto choose_cut = [&](const std::vector<int> &lev, const std::vector<char> &skip, int &maxlev) {
+        std::vector<long long> cnt;
+        for (int i = 0; i < N; ++i) if (!skip[i]) { if ((size_t)lev[i] >= cnt.size()) cnt.resize(lev[i] + 1, 0); cnt[lev[i]]++; }
+        maxlev = (int)cnt.size() - 1;
+        long long tail = 0;
+        int cut = maxlev + 1;
+        for (int l = maxlev; l >= 1; --l) { if (tail + cnt[l] > tail_rows_max) break; tail += cnt[l]; cut = l; }
+        return cut;
+    };
+    auto add_to = [](std::vector<std::pair<int, double>> &acc, int code, double v) { acc.emplace_back(code, v); };
+    auto compress = [](EncRow &r) {         // merge equal codes, keep first-appearance order
+        std::vector<std::pair<int, double>> out;
+        std::unordered_map<int, size_t> pos;
+        for (auto &x : r) {
+            auto it = pos.find(x.first);
+            if (it == pos.end()) { pos[x.first] = out.size(); out.push_back(x); }
+            else out[it->second].second += x.second;
+        }
+        r.swap(out);
+    };
+    double maxL = 1.0;
+    for (double v : Lrows.val) maxL = std::max(maxL, std::fabs(v));
+    std::vector<int> levf(N, 0), levb(N, 0);
+    std::unordered_map<int, EncRow> tailf, tailb;
+    {
+        // ---------------- forward ----------------
+        for (int i = 0; i < N; ++i) {
+            if (triv[i]) continue;
+            int lv = 0;
+            for (int64_t k = Lrows.ptr[i]; k < Lrows.ptr[i + 1]; ++k) { const int jx = Lrows.col[k]; if (!triv[jx]) lv = std::max(lv, levf[jx] + 1); }
+            levf[i] = lv;
+        }
+        int maxlev = 0;
+        int cut = choose_cut(levf, triv, maxlev);
+        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL"); ++attempt, cut += (maxlev - cut + 1) / 2) {
+            long long orig = 0, fill = 0;
+            double growth = 0.0;
+            bool okinv = true;
+            for (int t = 0; t < N && okinv; ++t) {
+                if (triv[t] || levf[t] < cut) continue;
+                EncRow acc;
+                for (int64_t k = Lrows.ptr[t]; k < Lrows.ptr[t + 1]; ++k) {
+                    const int jx = Lrows.col[k]; const double a = Lrows.val[k];
+                    ++orig;
+                    if (triv[jx]) add_to(acc, (int)(-(p[jx]) - 2), a);
+                    else if (levf[jx] >= cut) {
+                        add_to(acc, (int)(-(p[jx]) - 2), a);            // the z_j part of w_j
+                        for (auto &x : tailf[jx]) add_to(acc, x.first, -a * x.second);
+                    } else add_to(acc, jx, a);
+                }
+                compress(acc);
+                fill += (long long)acc.size();
+                for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
+                if (fill > tail_fill_max * std::max<long long>(orig, 1) + 1024 || growth > 1e3 * maxL || acc.size() > tail_len_max) okinv = false;
+                tailf[t] = std::move(acc);
+            }
+            if (!okinv) { tailf.clear(); continue; }
+            for (auto &kv : tailf) levf[kv.first] = cut;
+            break;
+        }
+        std::vector<SweepRow> rows;
+        for (int i = 0; i < N; ++i) {
+            if (triv[i]) continue;
+            auto it = tailf.find(i);
+            rows.push_back({i, levf[i], it == tailf.end() ? Lrows.len(i) : (int)it->second.size()});
+        }
+        sweep_append(W, rows, p, d, e, partner, g_grid_warps_hint,
+                     [&](int r) {
+                         auto it = tailf.find(r);
+                         if (it != tailf.end()) return it->second;
+                         EncRow er;
+                         for (int64_t k = Lrows.ptr[r]; k < Lrows.ptr[r + 1]; ++k) {
+                             const int jx = Lrows.col[k];
+                             er.emplace_back(triv[jx] ? (int)(-(p[jx]) - 2) : jx, Lrows.val[k]);
+                         }
+                         return er;
+                     },
+                     [&](int r) { return F_FWD | (fused[r] ? F_FUSED : 0); });
+        W.nfwd = W.nitems;
+        W.lev_f_eff = 0;
+        for (int i = 0; i < N; ++i) if (!triv[i]) W.lev_f_eff = std::max(W.lev_f_eff, levf[i] + 1);
+    }
+    {
+        // ---------------- backward: everything not finished in the forward sweep ----------------
+        for (int i = N - 1; i >= 0; --i) {
+            if (fused[i]) continue;
+            int lv = 0;
+            for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) { const int r = Lcols.col[k]; if (!fused[r]) lv = std::max(lv, levb[r] + 1); }
+            levb[i] = lv;
+        }
+        int maxlev = 0;
+        int cut = choose_cut(levb, fused, maxlev);
+        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL"); ++attempt, cut += (maxlev - cut + 1) / 2) {
+            bool tail_has_2x2 = false;
+            for (int i = 0; i < N; ++i) if (!fused[i] && levb[i] >= cut && partner[i] >= 0) tail_has_2x2 = true;
+            if (tail_has_2x2) continue;
+            long long orig = 0, fill = 0;
+            double growth = 0.0;
+            bool okinv = true;
+            for (int t = N - 1; t >= 0 && okinv; --t) {
+                if (fused[t] || levb[t] < cut) continue;
+                EncRow acc;
+                for (int64_t k = Lcols.ptr[t]; k < Lcols.ptr[t + 1]; ++k) {
+                    const int r = Lcols.col[k]; const double a = Lcols.val[k];
+                    ++orig;
+                    if (!fused[r] && levb[r] >= cut) {
+                        // y_r = w_r/d_r - sum(tail deps of r):  a*y_r
+                        add_to(acc, triv[r] ? (int)(-(p[r]) - 2) : N + r, a / d[r]);
+                        for (auto &x : tailb[r]) add_to(acc, x.first, -a * x.second);
+                    } else add_to(acc, r, a);
+                }
+                compress(acc);
+                fill += (long long)acc.size();
+                for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
+                if (fill > tail_fill_max * std::max<long long>(orig, 1) + 1024 || acc.size() > tail_len_max) okinv = false;
+                tailb[t] = std::move(acc);
+            }
+            // growth is judged against the scale of L'/D entries actually present
+            double scale = maxL;
+            for (auto &kv : tailb) scale = std::max(scale, maxL / std::max(std::fabs(d[kv.first]), 1e-300));
+            if (growth > 1e3 * scale) okinv = false;
+            if (!okinv) { tailb.clear(); continue; }
+            for (auto &kv : tailb) levb[kv.first] = cut;
+            break;
+        }
+        std::vector<SweepRow> rows;
+        for (int i = 0; i < N; ++i) {
+            if (fused[i]) continue;
+            auto it = tailb.find(i);
+            rows.push_back({i, levb[i], it == tailb.end() ? Lcols.len(i) : (int)it->second.size()});
+        }
+        sweep_append(W, rows, p, d, e, partner, g_grid_warps_hint,
+                     [&](int r) {
+                         auto it = tailb.find(r);
+                         if (it != tailb.end()) return it->second;
+                         EncRow er;
+                         for (int64_t k = Lcols.ptr[r]; k < Lcols.ptr[r + 1]; ++k) er.emplace_back(Lcols.col[k], Lcols.val[k]);
+                         return er;
+                     },
+                     [&](int r) { return (triv[r] ? F_WDIRECT : 0) | (hasR[r] ? F_STORE : 0) | (partner[r] >= 0 ? F_PARTNER : 0); });
+        W.lev_b_eff = 0;
+        for (int i = 0; i < N; ++i) if (!fused[i]) W.lev_b_eff = std::max(W.lev_b_eff, levb[i] + 1);
+        W.tail_f = (long long)tailf.size(); W.tail_b = (long long)tailb.size();
+    }
+    for (int i = 0; i < N; ++i) { W.n_trivial += triv[i]; W.n_fused += fused[i]; }
+    if ((int64_t)W.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
     // ---- K_P = [A B'; B C] by rows
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, (int)nA, (int)nC);
@@ -651,15 +989,13 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     CUDA_TRY(cudaSetDevice(device));
     DevLdl &m = o->d;
     m.N = N; m.nA = (int)nA; m.nC = (int)nC;
-    CUDA_TRY(upload_sweep(o->ar, Wf, m.fwd));
-    CUDA_TRY(upload_sweep(o->ar, Wb, m.bwd));
-    CUDA_TRY(o->ar.upload(&m.b_d, bd));
-    CUDA_TRY(o->ar.upload(&m.b_partner, bpart));
-    CUDA_TRY(o->ar.upload(&m.b_e, be));
-    CUDA_TRY(o->ar.upload(&m.b_dp, bdp));
+    CUDA_TRY(upload_sweep(o->ar, W, m.sw));
     CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));        // tag 0 = never produced; epochs start at 1
     CUDA_TRY(o->ar.alloc(&m.ybuf, N, true));
     CUDA_TRY(o->ar.alloc(&m.epoch, 1, true));
+    CUDA_TRY(o->ar.alloc(&m.wv, N, true));
+    CUDA_TRY(o->ar.alloc(&m.yv, N, true));
+    m.sync_free = getenv("CPK_LDL_SYNCFREE") ? atoi(getenv("CPK_LDL_SYNCFREE")) : 0;
     CUDA_TRY(upload_sell(o->ar, sKP, m.KP));
     CUDA_TRY(upload_sell(o->ar, sK12, m.K12));
     CUDA_TRY(upload_sell(o->ar, sK22, m.K22));
@@ -673,6 +1009,10 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     CUDA_TRY(o->ar.alloc(&o->d_y, N));
     CUDA_TRY(o->ar.alloc(&o->d_status, 1, true));
     o->nnz_off = Lrows.nnz(); o->lev_f = nlf; o->lev_b = nlb; o->n2x2 = n2;
+    if (getenv("CPK_VERBOSE"))
+        fprintf(stderr, "[cpk] LDL sweep: N=%d trivial=%lld fused=%lld items=%d (fwd %d) segments=%d levels L %d/%d -> effective %d/%d, tail rows inverted %lld/%lld, warp-rows %lld (longest row %lld), padded entries %zu\n",
+                N, (long long)W.n_trivial, (long long)W.n_fused, W.nitems, W.nfwd, (int)W.seg.size() / 3, nlf, nlb, W.lev_f_eff, W.lev_b_eff,
+                (long long)W.tail_f, (long long)W.tail_b, (long long)W.n_warprow, (long long)W.max_len, W.col.size());
     *out = register_obj(std::move(o));
     return CPK_OK;
 }
@@ -687,7 +1027,7 @@ static int ldl2_set(cpk_handle h, int which, double v)
         case 2: M->d.force_itref = (v != 0.0 && v != 1.0) ? 0 : (int)v; break;      // opLDL2.m:105-111
         case 3: M->d.residual_update = v != 0.0; break;
         case 4: M->d.ru_stateful = v != 0.0; break;
-        case 5: M->d.track_rnorm = v != 0.0; break;
+        case 5: M->d.track_rnorm = (int)v; break;
     }
     return CPK_OK;
 }
@@ -817,8 +1157,10 @@ static int run_matvec(int device, const DevSell &A, const double *x, double *y, 
     }
     CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
     const bool grid = use_grid(A.nrows);
-    if (grid) k_matvec<true><<<dc->grid_blocks, kBlock, 0, dc->stream>>>(A, dx, dy);
-    else      k_matvec<false><<<1, kBlock, 0, dc->stream>>>(A, dx, dy);
+    static const int ring_el = [] { const char *e = getenv("CPK_RING"); return e ? atoi(e) / 32 * 32 : 256; }();
+    const size_t rbytes = (size_t)kWarpsPerCta * kRingStages * 12 * ring_el;
+    if (grid) k_matvec<true><<<dc->grid_blocks, kBlock, rbytes, dc->stream>>>(A, dx, dy, ring_el);
+    else      k_matvec<false><<<1, kBlock, rbytes, dc->stream>>>(A, dx, dy, ring_el);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
@@ -870,6 +1212,14 @@ int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_h
     d.n = n; d.m = m; d.N = n + m;
     CUDA_TRY(upload_sell(o->ar, s, d.HC));
     d.Hn = d.HC; d.Hn.nrows = n; d.Hn.ncols = n; d.Hn.nslices = h_slices; d.Hn.nlong = h_long;
+    {
+        const int nw[2] = {g_grid_warps_hint, kWarpsPerCta};
+        for (int kdx = 0; kdx < 2; ++kdx) {
+            std::vector<int> sp = warp_split(s.sptr, h_slices, nw[kdx]);
+            CUDA_TRY(o->ar.upload(&d.Hn.wsplit[kdx], sp));
+            d.Hn.nws[kdx] = nw[kdx];
+        }
+    }
     CUDA_TRY(upload_sell(o->ar, sc, d.Cm));
     d.M = M->d;
     CUDA_TRY(o->ar.alloc(&o->d_sys, 1));
@@ -915,6 +1265,7 @@ struct Plan {
     long long gs;           // global scalar scratch doubles
     int wide_cols;
     int restart, mem;
+    int ring_off, ring_elems;
 };
 
 static int make_plan(int solver, const cpk_opts *o, Plan *p)
@@ -949,7 +1300,16 @@ static int make_plan(int solver, const cpk_opts *o, Plan *p)
         default: return fail(CPK_ERR_ARG, "unknown solver id %d", solver);
     }
     p->nvec += 2;
-    p->dsm = (p->dsm + 15) & ~(size_t)15;
+    p->dsm = (p->dsm + 127) & ~(size_t)127;
+    // per-warp bulk-copy rings behind the solver's scratch: as many entries per
+    // stage as fit (256 preferred), none if CPK_RING=0
+    static const int ring_pref = [] { const char *e = getenv("CPK_RING"); return e ? atoi(e) : 256; }();
+    p->ring_off = (int)p->dsm;
+    p->ring_elems = 0;
+    for (int el = ring_pref / 32 * 32; el >= 64; el -= 32) {
+        const size_t need = (size_t)kWarpsPerCta * kRingStages * 12 * el;
+        if (p->dsm + need <= 200 * 1024) { p->ring_elems = el; p->dsm += need; break; }
+    }
     return CPK_OK;
 }
 
@@ -1006,6 +1366,7 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
     a.work = S->d_work; a.work_len = (long long)plan.nvec * N;
     a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+    a.ring_off = plan.ring_off; a.ring_elems = plan.ring_elems;
     CUDA_TRY(cudaMemcpyAsync(S->d_args, &a, sizeof a, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = S->d_sys; const SolveArgs *pa = S->d_args;
@@ -1089,6 +1450,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
         a.work = S->d_work; a.work_len = (long long)plan.nvec * S->h.N;
         a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+        a.ring_off = plan.ring_off; a.ring_elems = plan.ring_elems;
         hargs[i] = a;
         CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     }

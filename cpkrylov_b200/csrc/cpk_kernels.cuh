@@ -30,25 +30,145 @@ struct PhaseClock {
 // Epi is called as epi(row, sum) by the lane that owns the row.
 // ---------------------------------------------------------------------------
 template <class Team, class Epi>
-__device__ __forceinline__ void spmv_sell(const Team &T, const DevSell &A, const double *x, Epi &&epi)
+__device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
-    for (int s = T.gwarp; s < A.nslices; s += T.nwarps) {
-        const int beg = __ldg(&A.sptr[s]);
-        const int end = __ldg(&A.sptr[s + 1]);
-        const int row = __ldg(&A.rowmap[s * 32 + T.lane]);
-        double acc = 0.0;
-        int k = beg + T.lane;
-        // 4 entries in flight per lane; the adds stay in row order
-        for (; k + 96 < end; k += 128) {
-            const int c0 = __ldg(&A.col[k]),      c1 = __ldg(&A.col[k + 32]);
-            const int c2 = __ldg(&A.col[k + 64]), c3 = __ldg(&A.col[k + 96]);
-            const double v0 = __ldg(&A.val[k]),      v1 = __ldg(&A.val[k + 32]);
-            const double v2 = __ldg(&A.val[k + 64]), v3 = __ldg(&A.val[k + 96]);
-            const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
-            acc += v0 * x0; acc += v1 * x1; acc += v2 * x2; acc += v3 * x3;
+    // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
+    // range are one contiguous span, walked in chunks of 4 entries per lane with
+    // the next chunk's loads issued before the current chunk's x-gathers are
+    // consumed (register double buffering), so HBM latency is off the per-slice
+    // critical path.  Slice ends come from sptr, prefetched one slice ahead.
+    int sa, sb;
+    {
+        const int *split = A.wsplit[Team::kKind];
+        if (split != nullptr && A.nws[Team::kKind] == T.nwarps) {
+            sa = __ldg(&split[T.gwarp]); sb = __ldg(&split[T.gwarp + 1]);
+        } else {
+            sa = (int)((long long)A.nslices * T.gwarp / T.nwarps);
+            sb = (int)((long long)A.nslices * (T.gwarp + 1) / T.nwarps);
         }
-        for (; k < end; k += 32) acc += __ldg(&A.val[k]) * x[__ldg(&A.col[k])];
-        if (row >= 0) epi(row, acc);
+    }
+    if (sa < sb && T.ring.base != nullptr) {
+        // ---- bulk-copy ring path: (val, col) of the span arrive in shared memory ----
+        WarpRing &R = T.ring;
+        const int SE = R.elems;                 // entries per stage
+        int s = sa;
+        const int ka = __ldg(&A.sptr[sa]);
+        const int kb = __ldg(&A.sptr[sb]);
+        int send = __ldg(&A.sptr[s + 1]);
+        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+        int row = __ldg(&A.rowmap[s * 32 + T.lane]);
+        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+        double acc = 0.0;
+        const int nch = (kb - ka + SE - 1) / SE;
+        auto post = [&](int j) {                // lane 0: request chunk j into its stage
+            const unsigned st = (R.n + (unsigned)j) % kRingStages;
+            const int k0 = ka + j * SE;
+            const unsigned ne = (unsigned)min(SE, kb - k0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&R.bar[st], ne * 12u);
+            bulk_g2s(R.val(st), &A.val[k0], ne * 8u, &R.bar[st]);
+            bulk_g2s(R.col(st), &A.col[k0], ne * 4u, &R.bar[st]);
+        };
+        if (T.lane == 0)
+            for (int j = 0; j < kRingStages && j < nch; ++j) post(j);
+        for (int j = 0; j < nch; ++j) {
+            const unsigned use = R.n + (unsigned)j;
+            const unsigned st = use % kRingStages, par = (use / kRingStages) & 1u;
+            {
+                long long t0 = clock64();
+                unsigned spins = 0;
+                while (!mbar_try_wait(&R.bar[st], par)) {
+                    if ((++spins & 0x3ff) == 0 && clock64() - t0 > kWatchdogCycles) { T.set_abort(); break; }
+                }
+            }
+            const double *sv = R.val(st);
+            const int *sc = R.col(st);
+            const int k0 = ka + j * SE;
+            const int ne = min(SE, kb - k0);
+            for (int e0 = 0; e0 < ne; e0 += 256) {          // 8 entries per lane at a time
+                int cc[8]; double vv[8], xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + 32 * u + T.lane;
+                    if (e < ne) { cc[u] = sc[e]; vv[u] = sv[e]; } else { cc[u] = -1; vv[u] = 0.0; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xv[u] = (cc[u] >= 0) ? x[cc[u]] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int kk0 = k0 + e0 + 32 * u;       // warp-uniform
+                    if (e0 + 32 * u < ne) {
+                        while (kk0 >= send) {               // slice s is complete (possibly empty ones follow)
+                            if (row >= 0) epi(row, acc);
+                            acc = 0.0; ++s;
+                            send = send2; row = row2;
+                            send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+                            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+                        }
+                        acc += vv[u] * xv[u];
+                    }
+                }
+            }
+            __syncwarp();
+            if (T.lane == 0 && j + kRingStages < nch) post(j + kRingStages);
+        }
+        R.n += (unsigned)nch;
+        while (s < sb) {
+            if (row >= 0) epi(row, acc);
+            acc = 0.0; ++s;
+            row = row2;
+            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+        }
+    } else if (sa < sb) {
+        int s = sa;
+        int k = __ldg(&A.sptr[sa]);
+        const int kb = __ldg(&A.sptr[sb]);
+        int send = __ldg(&A.sptr[s + 1]);
+        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+        int row = __ldg(&A.rowmap[s * 32 + T.lane]);
+        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+        double acc = 0.0;
+        constexpr int U = 8;            // entries per lane in flight (x2: current + prefetched chunk)
+        int cc[U]; double vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int kk = k + 32 * u + T.lane;
+            if (kk < kb) { cc[u] = __ldg(&A.col[kk]); vv[u] = __ldg(&A.val[kk]); } else { cc[u] = 0; vv[u] = 0.0; }
+        }
+        while (k < kb) {
+            int cn[U]; double vn[U], xv[U];
+            const int k2 = k + 32 * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = k2 + 32 * u + T.lane;
+                if (kk < kb) { cn[u] = __ldg(&A.col[kk]); vn[u] = __ldg(&A.val[kk]); } else { cn[u] = 0; vn[u] = 0.0; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = (k + 32 * u < kb) ? x[cc[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k0 = k + 32 * u;                  // warp-uniform
+                if (k0 < kb) {
+                    while (k0 >= send) {                    // slice s is complete (possibly empty ones follow)
+                        if (row >= 0) epi(row, acc);
+                        acc = 0.0; ++s;
+                        send = send2; row = row2;
+                        send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+                    }
+                    acc += vv[u] * xv[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { cc[u] = cn[u]; vv[u] = vn[u]; }
+            k = k2;
+        }
+        while (s < sb) {
+            if (row >= 0) epi(row, acc);
+            acc = 0.0; ++s;
+            row = row2;
+            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+        }
     }
     // long rows: one warp per row, lane-strided partial sums + butterfly
     for (int r = T.gwarp; r < A.nlong; r += T.nwarps) {
@@ -80,108 +200,305 @@ struct VecIn {
     }
 };
 
-// ---------------------------------------------------------------------------
-// y = P * L^-T * D^-1 * L^-1 * P' * in        (opLDL2.m:86, right to left)
-//
-// One sweep, no barrier inside: the forward items (rows of L in dependency-
-// level order) are followed by the backward items (D-solve fused into the row
-// of L'); every produced value carries a ready flag (= the epoch of this solve)
-// and every consumer polls the flags of what it needs.  A warp takes items in
-// increasing order, all warps of the team are resident (cooperative launch or
-// one CTA), and an item only depends on lower-numbered items, so the sweep
-// cannot deadlock; wait loops never block a lane on another lane of its warp.
-// If `accumulate`, out[p] += y (the y = y + dy of opLDL2.m:181).
-// Ends WITHOUT a team barrier: the caller syncs before `out` is gathered.
-// ---------------------------------------------------------------------------
-template <class Team>
-__device__ __noinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn &in, double *out, bool accumulate, int epoch_i)
+struct ItemMeta { int beg, end, slot, rid, pidx, flags; double d; };
+struct ItemChunk { int c[4]; double v[4]; };
+
+__device__ __forceinline__ void item_load(const DevSweep &S, int t, int lane, ItemMeta &m, ItemChunk &r)
 {
-    const unsigned long long epoch = (unsigned long long)(unsigned)epoch_i;
-    const int nf = M.fwd.nitems, nb = M.bwd.nitems;
-    for (int it = T.gwarp; it < nf + nb; it += T.nwarps) {
-        const bool fwd = it < nf;
-        const DevSweep &S = fwd ? M.fwd : M.bwd;
-        const int s = fwd ? it : it - nf;
-        const int beg = __ldg(&S.sptr[s]);
-        const int end = __ldg(&S.sptr[s + 1]);
-        const int slot = s * 32 + T.lane;
-        const int rid = __ldg(&S.rid[slot]);
-        bool done = rid < 0;
-        int k = beg + T.lane;
-        double acc = 0.0;
-        int stage = 0;          // backward rows: 0 = still waiting for own (and partner) w
-        int pidx = 0, partner = -1;
-        double dd = 1.0;
-        const Tagged *dep = fwd ? M.wbuf : M.ybuf;
-        if (!done) {
-            pidx = __ldg(&S.pidx[slot]);
-            if (fwd) { acc = in(pidx); stage = 1; }
-            else { partner = __ldg(&M.b_partner[slot]); dd = __ldg(&M.b_d[slot]); }
-        }
+    m.beg = __ldg(&S.sptr[t]);
+    m.end = __ldg(&S.sptr[t + 1]);
+    m.slot = t * 32 + lane;
+    m.rid = __ldg(&S.rid[m.slot]);
+    m.pidx = __ldg(&S.pidx[m.slot]);
+    m.flags = __ldg(&S.flags[m.slot]);
+    m.d = __ldg(&S.d[m.slot]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int kk = m.beg + 32 * u + lane;
+        if (kk < m.end) { r.c[u] = __ldg(&S.col[kk]); r.v[u] = __ldg(&S.val[kk]); }
+        else { r.c[u] = -1; r.v[u] = 0.0; }
+    }
+}
+
+// Spin until the tagged value carries this solve's epoch (lanes of one item never
+// depend on one another, so a per-lane blocking wait cannot deadlock).
+template <class Team>
+__device__ __forceinline__ double wait_tagged(const Team &T, const Tagged *p, unsigned long long epoch)
+{
+    Tagged tg = ld_tagged(p);
+    if (tg.tag != epoch) {
         long long t0 = clock64();
-        unsigned spins = 0;
-        for (;;) {
-            if (!done) {
-                if (stage == 0) {
-                    // D-solve on entry of the backward row (opLDL2.m:86, inv(op.D))
-                    const Tagged w = ld_tagged(&M.wbuf[rid]);
-                    if (partner < 0) {
-                        if (w.tag == epoch) { acc = w.v / dd; stage = 1; }
-                    } else {
-                        const Tagged wp = ld_tagged(&M.wbuf[partner]);
-                        if (w.tag == epoch && wp.tag == epoch) {
-                            const double e = __ldg(&M.b_e[slot]);
-                            const double dp = __ldg(&M.b_dp[slot]);
-                            const double det = dd * dp - e * e;
-                            acc = (dp * w.v - e * wp.v) / det;
-                            stage = 1;
-                        }
-                    }
-                }
-                if (stage == 1) {
-                    // up to 4 dependencies in flight; consumed strictly in row order
-                    while (k < end) {
-                        int c[4]; double v[4]; Tagged t[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) c[u] = (k + 32 * u < end) ? __ldg(&S.col[k + 32 * u]) : -1;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (c[u] >= 0) { v[u] = __ldg(&S.val[k + 32 * u]); t[u] = ld_tagged(&dep[c[u]]); }
-                            else { v[u] = 0.0; t[u].v = 0.0; t[u].tag = epoch; }
-                        }
-                        bool stalled = false;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (stalled) continue;
-                            if (c[u] < 0) { k = end; stalled = true; }
-                            else if (t[u].tag == epoch) { acc -= v[u] * t[u].v; k += 32; }
-                            else stalled = true;
-                        }
-                        if (stalled) break;
-                    }
-                    if (k >= end) {
-                        if (fwd) {
-                            st_tagged(&M.wbuf[rid], acc, epoch);
-                        } else {
-                            st_tagged(&M.ybuf[rid], acc, epoch);
-                            if (accumulate) out[pidx] = out[pidx] + acc; else out[pidx] = acc;
-                        }
-                        done = true;
-                    }
-                }
-            }
-            if (__all_sync(FULL, done)) break;
+        unsigned spins = 0, ns = 32;
+        do {
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
+            tg = ld_tagged(p);
             if ((++spins & 0x3f) == 0) {
                 if (T.aborted()) break;
                 if (clock64() - t0 > kWatchdogCycles) { T.set_abort(); break; }
+            }
+        } while (tg.tag != epoch);
+    }
+    return tg.v;
+}
+
+// One item.  TAGGED: sync-free walk (values carry their epoch and are polled);
+// otherwise level-synchronous walk (plain values, levels separated by barriers).
+template <bool TAGGED, class Team>
+__device__ __forceinline__ void item_process(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
+                                             unsigned long long epoch, const ItemMeta &m, const ItemChunk &r)
+{
+    const DevSweep &S = M.sw;
+    const int Nn = M.N;                 // backward rows: code c >= N addresses the forward result w[c - N]
+    const int f0 = __shfl_sync(FULL, m.flags, 0);
+    const bool warprow = (f0 & F_WARPROW) != 0;
+    const bool isfwd = (f0 & F_FWD) != 0;       // uniform over an item
+    const bool live = m.rid >= 0;
+
+    // value of dependency code c (c >= 0), blocking until published when TAGGED
+    auto dep_value = [&](int c) -> double {
+        if (TAGGED) {
+            const Tagged *src = (c >= Nn) ? &M.wbuf[c - Nn] : (isfwd ? &M.wbuf[c] : &M.ybuf[c]);
+            return wait_tagged(T, src, epoch);
+        } else {
+            return (c >= Nn) ? M.wv[c - Nn] : (isfwd ? M.wv[c] : M.yv[c]);
+        }
+    };
+    // ---- sum over the row's entries, 4 per lane in flight, first 4 prefetched --------
+    double sum = 0.0;                   // = - sum_j val_j * value_j, accumulated in storage order
+    {
+        int c[4]; double v[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c[u] = r.c[u]; v[u] = r.v[u]; }
+        int base = m.beg;
+        for (;;) {
+            if (TAGGED) {
+                // issue all tagged loads first, wait (re-poll) afterwards
+                Tagged tg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c[u] >= 0) tg[u] = ld_tagged((c[u] >= Nn) ? &M.wbuf[c[u] - Nn] : (isfwd ? &M.wbuf[c[u]] : &M.ybuf[c[u]]));
+                    else { tg[u].v = (c[u] <= -2) ? in(-c[u] - 2) : 0.0; tg[u].tag = epoch; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = (tg[u].tag == epoch) ? tg[u].v : dep_value(c[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = (c[u] >= 0) ? dep_value(c[u]) : ((c[u] <= -2) ? in(-c[u] - 2) : 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u] != -1) sum -= v[u] * x[u];
+            base += 128;
+            if (base >= m.end) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = base + 32 * u + T.lane;
+                if (kk < m.end) { c[u] = __ldg(&S.col[kk]); v[u] = __ldg(&S.val[kk]); } else { c[u] = -1; v[u] = 0.0; }
+            }
+        }
+    }
+    if (warprow) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (T.lane != 0) return;
+    } else if (!live) return;
+    // ---- base value: (P'z)_i for a forward row, D-solve on entry of a backward row ----
+    double acc;
+    if (isfwd) acc = in(m.pidx);
+    else {
+        double w;
+        if (m.flags & F_WDIRECT) w = in(m.pidx);
+        else w = TAGGED ? wait_tagged(T, &M.wbuf[m.rid], epoch) : M.wv[m.rid];
+        if (!(m.flags & F_PARTNER)) acc = w / m.d;                          // opLDL2.m:86, inv(op.D)
+        else {
+            const int partner = __ldg(&S.partner[m.slot]);
+            const double wp = TAGGED ? wait_tagged(T, &M.wbuf[partner], epoch) : M.wv[partner];
+            const double e = __ldg(&S.e[m.slot]);
+            const double dp = __ldg(&S.dp[m.slot]);
+            const double det = m.d * dp - e * e;
+            acc = (dp * w - e * wp) / det;
+        }
+    }
+    acc += sum;
+    // ---- publish -------------------------------------------------------------------------
+    if (isfwd && !(m.flags & F_FUSED)) {
+        if (TAGGED) st_tagged(&M.wbuf[m.rid], acc, epoch); else M.wv[m.rid] = acc;
+    } else {
+        if (isfwd) acc = acc / m.d;                 // F_FUSED: column of L is empty, y_i = w_i / d_i
+        if (isfwd || (m.flags & F_STORE)) { if (TAGGED) st_tagged(&M.ybuf[m.rid], acc, epoch); else M.yv[m.rid] = acc; }
+        if (accumulate) out[m.pidx] = out[m.pidx] + acc; else out[m.pidx] = acc;
+    }
+}
+
+// Sync-free walk: no barrier inside.  Every produced value is published with
+// the epoch of this solve in one 128-bit store; consumers re-poll until the tag
+// matches.  Items only depend on lower-numbered items, every warp walks its
+// items in increasing order and all warps of the team are resident, so the walk
+// cannot deadlock.  Used when a sweep is too deep for one barrier per level.
+template <class Team>
+__device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate, int epoch_i)
+{
+    const unsigned long long epoch = (unsigned long long)(unsigned)epoch_i;
+    const DevSweep &S = M.sw;
+    for (int g = 0; g < S.nseg; ++g) {
+        const int sbeg = __ldg(&S.seg[3 * g]), send = __ldg(&S.seg[3 * g + 1]), blk = __ldg(&S.seg[3 * g + 2]);
+        const int nblk = (send - sbeg + blk - 1) / blk;
+        for (int b = T.gwarp; b < nblk; b += T.nwarps) {
+            int t = sbeg + b * blk;
+            const int tend = min(send, t + blk);
+            ItemMeta m0; ItemChunk r0;
+            item_load(S, t, T.lane, m0, r0);
+            for (; t < tend; ++t) {
+                ItemMeta m1; ItemChunk r1;
+                if (t + 1 < tend) item_load(S, t + 1, T.lane, m1, r1);
+                item_process<true>(T, M, in, out, accumulate, epoch, m0, r0);
+                m0 = m1; r0 = r1;
             }
         }
     }
 }
 
+// Level-synchronous walk of the same item list: one team barrier per dependency
+// level, plain 8-byte values, no polling.  Inside a level every warp streams a
+// contiguous range of items with the next item's row prefetched.  This is the
+// default: after the setup-time shortcuts (trivial / fused rows, tail inversion)
+// the sweeps of a KKT preconditioner have a handful of levels.
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Pull the lines of item t into L2 ahead of use (no registers, no shared memory):
+// lane i fetches the i-th 128-byte line of the item's per-slot arrays / entries.
+__device__ __forceinline__ void item_prefetch(const DevSweep &S, int t, int lane)
+{
+    const int slot0 = t * 32;
+    const char *p = nullptr;
+    switch (lane) {
+        case 0: p = (const char *)&S.rid[slot0]; break;
+        case 1: p = (const char *)&S.pidx[slot0]; break;
+        case 2: p = (const char *)&S.flags[slot0]; break;
+        case 3: p = (const char *)&S.d[slot0]; break;
+        case 4: p = (const char *)&S.d[slot0 + 16]; break;
+        case 5: p = (const char *)&S.sptr[t]; break;
+        default: break;
+    }
+    if (p) prefetch_l2(p);
+}
+__device__ __forceinline__ void item_prefetch_entries(const DevSweep &S, int kbeg, int kend, int lane)
+{
+    // entries [kbeg, kend): col 4 B, val 8 B per entry -> one line per 32 / 16 entries
+    const int ncl = (kend - kbeg + 31) / 32, nvl = (kend - kbeg + 15) / 16;
+    if (lane < ncl) prefetch_l2(&S.col[kbeg + lane * 32]);
+    else if (lane - ncl < nvl) prefetch_l2(&S.val[kbeg + (lane - ncl) * 16]);
+}
+
+// Level-synchronous walk of the item list: one team barrier per dependency
+// level, plain 8-byte values, no polling.  Inside a level every warp owns a
+// contiguous range of items and walks it in batches of 4: all row data of the
+// batch is requested first, then all gathers, then the arithmetic -- three
+// memory round trips per batch instead of three per item.  Items that are not
+// "simple" (rows longer than 2 entries, warp-rows, 2x2 pivots) take the generic
+// per-item path.
+template <class Team>
+__device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
+                                              PhaseClock *dbg = nullptr)
+{
+    const DevSweep &S = M.sw;
+    constexpr int B = 4;
+    const int Nn = M.N;
+    for (int g = 0; g < S.nlev; ++g) {
+        const int a = __ldg(&S.levptr[g]), b = __ldg(&S.levptr[g + 1]);
+        const long long cnt = b - a;
+        int t = a + (int)(cnt * T.gwarp / T.nwarps);
+        const int tend = a + (int)(cnt * (T.gwarp + 1) / T.nwarps);
+        while (t < tend) {
+            const int nb = min(B, tend - t);
+            // ---- stage A: row data of the whole batch -------------------------------
+            int beg[B], wid[B], rid[B], pidx[B], flg[B], c0[B], c1[B];
+            double dd[B], v0[B], v1[B];
+#pragma unroll
+            for (int q = 0; q < B; ++q) {
+                if (q < nb) {
+                    beg[q] = __ldg(&S.sptr[t + q]);
+                    wid[q] = __ldg(&S.sptr[t + q + 1]) - beg[q];
+                    const int slot = (t + q) * 32 + T.lane;
+                    rid[q] = __ldg(&S.rid[slot]); pidx[q] = __ldg(&S.pidx[slot]);
+                    flg[q] = __ldg(&S.flags[slot]); dd[q] = __ldg(&S.d[slot]);
+                } else { beg[q] = 0; wid[q] = 0; rid[q] = -1; pidx[q] = 0; flg[q] = 0; dd[q] = 1.0; }
+            }
+            bool simple = true;
+#pragma unroll
+            for (int q = 0; q < B; ++q) simple = simple && wid[q] <= 64 && !(flg[q] & (F_PARTNER | F_WARPROW));
+            simple = __all_sync(FULL, simple);
+            if (simple) {
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
+                    if (wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + T.lane]); v0[q] = __ldg(&S.val[beg[q] + T.lane]); }
+                    if (wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + T.lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + T.lane]); }
+                }
+                // ---- stage B: gathers ---------------------------------------------------
+                double base[B], x0[B], x1[B];
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    const bool isfwd = (flg[q] & F_FWD) != 0;
+                    base[q] = 0.0; x0[q] = 0.0; x1[q] = 0.0;
+                    if (rid[q] >= 0) {
+                        base[q] = (isfwd || (flg[q] & F_WDIRECT)) ? in(pidx[q]) : M.wv[rid[q]];
+                        const double *depv = isfwd ? M.wv : M.yv;
+                        if (c0[q] >= 0) x0[q] = (c0[q] >= Nn) ? M.wv[c0[q] - Nn] : depv[c0[q]];
+                        else if (c0[q] <= -2) x0[q] = in(-c0[q] - 2);
+                        if (c1[q] >= 0) x1[q] = (c1[q] >= Nn) ? M.wv[c1[q] - Nn] : depv[c1[q]];
+                        else if (c1[q] <= -2) x1[q] = in(-c1[q] - 2);
+                    }
+                }
+                // ---- stage C: arithmetic and publication -----------------------------------
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    if (rid[q] < 0) continue;
+                    const bool isfwd = (flg[q] & F_FWD) != 0;
+                    double acc = isfwd ? base[q] : base[q] / dd[q];     // D-solve on entry of a backward row
+                    double sum = 0.0;
+                    if (c0[q] != -1) sum -= v0[q] * x0[q];
+                    if (c1[q] != -1) sum -= v1[q] * x1[q];
+                    acc += sum;
+                    if (isfwd && !(flg[q] & F_FUSED)) M.wv[rid[q]] = acc;
+                    else {
+                        if (isfwd) acc = acc / dd[q];
+                        if (isfwd || (flg[q] & F_STORE)) M.yv[rid[q]] = acc;
+                        if (accumulate) out[pidx[q]] = out[pidx[q]] + acc; else out[pidx[q]] = acc;
+                    }
+                }
+            } else {
+                for (int q = 0; q < nb; ++q) {
+                    ItemMeta m; ItemChunk r;
+                    item_load(S, t + q, T.lane, m, r);
+                    item_process<false>(T, M, in, out, accumulate, 0ull, m, r);
+                }
+            }
+            t += nb;
+        }
+        if (dbg) dbg->mark(min(2 * g, 6));
+        if (g + 1 < S.nlev) T.sync();       // the caller syncs after the last level
+        if (dbg) dbg->mark(min(2 * g + 1, 7));
+    }
+}
+
+// y = P * L^-T * D^-1 * L^-1 * P' * in   (opLDL2.m:86, right to left).
+// If `accumulate`, out[p] += y (the y = y + dy of opLDL2.m:181).  Ends WITHOUT a
+// team barrier: the caller syncs before `out` is gathered.
+template <class Team>
+__device__ __forceinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate, int epoch)
+{
+    if (M.sync_free) ldl_solve_syncfree(T, M, in, out, accumulate, epoch);
+    else ldl_solve_levels(T, M, in, out, accumulate, (PhaseClock *)nullptr);
+}
+
 // r = xin - K*y with partial sums of r'r (and xin'xin): opLDL2.m:175-177,182-183
 template <class Team>
-__device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecIn &xin, const double *y,
+__device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecIn xin, const double *y,
                                             double *r, double &rr, double &xx, bool want_xx)
 {
     rr = 0.0; xx = 0.0;
@@ -200,7 +517,7 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
 // Exit : y complete and visible (ends with a team barrier).
 // ---------------------------------------------------------------------------
 template <class Team>
-__device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn &xin, double *y, int &epoch,
+__device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xin, double *y, int &epoch,
                            DevStatus *st, PhaseClock &pc)
 {
     const int n = M.nA;

@@ -785,15 +785,30 @@ __global__ void __launch_bounds__(kBlock, 1)
 k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols)
 {
     __shared__ TeamShared sh;
+    // the operator descriptors are read all the time: keep a CTA-local copy in
+    // shared memory (global copies would miss in L1 after every barrier)
+    __shared__ DevSystem s_sys;
+    __shared__ SolveArgs s_args;
+    {
+        const int idx = GRID ? 0 : blockIdx.x;
+        const int *src = reinterpret_cast<const int *>(sys + idx);
+        int *dst = reinterpret_cast<int *>(&s_sys);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevSystem) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const int *>(args + idx);
+        dst = reinterpret_cast<int *>(&s_args);
+        for (int i = threadIdx.x; i < (int)(sizeof(SolveArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    char *ring = s_args.ring_elems > 0 ? reinterpret_cast<char *>(g_dsm) + s_args.ring_off : nullptr;
     if (GRID) {
         GridTeam T;
-        T.init(ctl, partials, &sh);
+        T.init(ctl, partials, &sh, ring, s_args.ring_elems);
         T.wide = wide; T.wide_cols = wide_cols;
-        solve_entry<SOLVER>(T, sys[0], args[0], g_dsm);
+        solve_entry<SOLVER>(T, s_sys, s_args, g_dsm);
     } else {
         CtaTeam T;
-        T.init(ctl + blockIdx.x, nullptr, &sh);
-        solve_entry<SOLVER>(T, sys[blockIdx.x], args[blockIdx.x], g_dsm);
+        T.init(ctl + blockIdx.x, nullptr, &sh, ring, s_args.ring_elems);
+        solve_entry<SOLVER>(T, s_sys, s_args, g_dsm);
     }
 }
 
