@@ -143,8 +143,6 @@ struct SolveArgs {
     long long hist_cap;
     double *gs;             // GMRES/DQGMRES scalar scratch in global memory
     DevStatus *status;
-    int     ring_off;       // byte offset of the per-warp bulk-copy rings in dynamic shared memory
-    int     ring_elems;     // entries per ring stage (0: rings disabled)
 };
 
 // ---------------------------------------------------------------------------
@@ -210,59 +208,9 @@ constexpr long long kWatchdogCycles = 4000000000LL;   // ~2 s of SM clocks
 //   CtaTeam : a single CTA (small systems; a batch launch runs many of them)
 // Both expose: tid/nthreads, gwarp/nwarps/lane, sync(), reduce<K>().
 // ---------------------------------------------------------------------------
-constexpr int kRingStages = 4;      // bulk-copy stages in flight per warp
-
 struct TeamShared {
     double red[kWarpsPerCta][kRedMax];
     double out[kRedMax];
-    unsigned long long ringbar[kWarpsPerCta][kRingStages];     // mbarriers of the per-warp rings
-};
-
-// ---------------------------------------------------------------------------
-// Per-warp shared-memory ring fed by the bulk-copy (TMA) engine.  A warp streams
-// a contiguous span of a matrix (val[], col[]) through kRingStages stages of
-// `elems` entries: lane 0 posts cp.async.bulk copies that complete on the
-// stage's mbarrier, the 32 lanes wait on it and read their entries from shared
-// memory.  The copies in flight (stages x 12 B x elems per warp) are what covers
-// the HBM latency; no registers and no other warp are involved.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-struct WarpRing {
-    char *base;                 // this warp's stages (shared memory), nullptr = ring disabled
-    unsigned long long *bar;    // this warp's kRingStages mbarriers
-    int elems;                  // entries per stage, multiple of 32
-    unsigned n;                 // stage uses so far (selects stage and mbarrier phase)
-
-    __device__ void init(char *dsm_ring, int elems_, TeamShared *sh) {
-        const int w = threadIdx.x >> 5;
-        elems = elems_;
-        n = 0;
-        bar = sh ? sh->ringbar[w] : nullptr;
-        base = (dsm_ring && elems_ > 0 && sh) ? dsm_ring + (size_t)w * kRingStages * 12 * elems_ : nullptr;
-        if (base && (threadIdx.x & 31) == 0)
-            for (int i = 0; i < kRingStages; ++i) mbar_init(&bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncthreads();
-    }
-    __device__ __forceinline__ double *val(int st) const { return reinterpret_cast<double *>(base + (size_t)st * 12 * elems); }
-    __device__ __forceinline__ int *col(int st) const { return reinterpret_cast<int *>(base + (size_t)st * 12 * elems + (size_t)8 * elems); }
 };
 
 struct GridTeam {
@@ -273,10 +221,8 @@ struct GridTeam {
     TeamShared *sh;
     unsigned bar_target;
     unsigned red_parity;
-    WarpRing ring;
 
-    __device__ void init(TeamCtl *c, double *p, TeamShared *s, char *dsm_ring = nullptr, int ring_elems = 0) {
-        ring.init(dsm_ring, ring_elems, s);
+    __device__ void init(TeamCtl *c, double *p, TeamShared *s) {
         tid = blockIdx.x * blockDim.x + threadIdx.x;
         nthreads = gridDim.x * blockDim.x;
         gwarp = tid >> 5;
@@ -400,10 +346,8 @@ struct CtaTeam {
     int tid, nthreads, gwarp, nwarps, lane;
     TeamCtl *ctl;
     TeamShared *sh;
-    WarpRing ring;
 
-    __device__ void init(TeamCtl *c, double *, TeamShared *s, char *dsm_ring = nullptr, int ring_elems = 0) {
-        ring.init(dsm_ring, ring_elems, s);
+    __device__ void init(TeamCtl *c, double *, TeamShared *s) {
         tid = threadIdx.x;
         nthreads = blockDim.x;
         gwarp = tid >> 5;
@@ -468,5 +412,61 @@ struct CtaTeam {
 };
 
 #define TEAM_FOR(T, i, N) for (int i = (T).tid; i < (N); i += (T).nthreads)
+
+// Element-wise team loop over N elements with NIN input vectors:
+//   body(i, v) with v[k] = src[k][i]
+// Loads are 16-byte (two elements) when N is even and every vector is 16-byte
+// aligned, and a thread has 4 such loads per vector in flight before the first
+// body runs: ~90 KB per SM must be in flight to cover the HBM latency.
+template <int NIN, class Team, class Body>
+__device__ __forceinline__ void team_map(const Team &T, int N, const double *const (&src)[NIN], Body &&body)
+{
+    const int nt = T.nthreads;
+    bool vec = (N & 1) == 0;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) vec = vec && ((reinterpret_cast<unsigned long long>(src[k]) & 15ull) == 0);
+    if (vec) {
+        const int N2 = N >> 1;
+        for (int j0 = T.tid; j0 < N2; j0 += 4 * nt) {
+            double2 v[4][NIN];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * nt;
+                if (j < N2) {
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k) v[u][k] = reinterpret_cast<const double2 *>(src[k])[j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * nt;
+                if (j < N2) {
+                    double a[NIN], b[NIN];
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k) { a[k] = v[u][k].x; b[k] = v[u][k].y; }
+                    body(2 * j, a);
+                    body(2 * j + 1, b);
+                }
+            }
+        }
+    } else {
+        for (int i0 = T.tid; i0 < N; i0 += 4 * nt) {
+            double v[4][NIN];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nt;
+                if (i < N) {
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k) v[u][k] = src[k][i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nt;
+                if (i < N) body(i, v[u]);
+            }
+        }
+    }
+}
 
 }  // namespace cpk

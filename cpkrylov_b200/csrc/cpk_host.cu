@@ -567,7 +567,7 @@ static const void *solver_kernel(int solver, bool grid)
 }
 template <bool GRID> __global__ void k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st,
                                              TeamCtl *ctl, double *partials);
-template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y, int ring_elems);
+template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y);
 
 static int get_device_ctx(int device, DeviceCtx **out)
 {
@@ -596,8 +596,6 @@ static int get_device_ctx(int device, DeviceCtx **out)
         for (int g = 0; g < 2; ++g) {
             const void *k = solver_kernel(sv, g);
             CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
@@ -696,19 +694,50 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
 
 template <bool GRID>
 __global__ void __launch_bounds__(kBlock, 1)
-k_matvec(DevSell A, const double *x, double *y, int ring_elems)
+k_matvec(DevSell A, const double *x, double *y)
 {
-    __shared__ TeamShared sh;
-    __shared__ TeamCtl dummy;       // only the watchdog flag of a stand-alone launch
-    if (threadIdx.x == 0) { dummy.bar = 0; dummy.abort = 0; }
-    char *ring = ring_elems > 0 ? reinterpret_cast<char *>(g_dsm) : nullptr;
     if (GRID) {
-        GridTeam T; T.init(&dummy, nullptr, &sh, ring, ring_elems);
+        GridTeam T; T.init(nullptr, nullptr, nullptr);
         spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
     } else {
-        CtaTeam T; T.init(&dummy, nullptr, &sh, ring, ring_elems);
+        CtaTeam T; T.init(nullptr, nullptr, nullptr);
         spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
     }
+}
+
+// debug: latency of the team barrier and of a 1-value team reduction
+__global__ void __launch_bounds__(kBlock, 1) k_barrier_bench(TeamCtl *ctl, double *partials, int iters, long long *out)
+{
+    __shared__ TeamShared sh;
+    GridTeam T; T.init(ctl, partials, &sh);
+    T.sync();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) T.sync();
+    long long t1 = clock64();
+    double v[1] = {1.0};
+    for (int i = 0; i < iters; ++i) { T.template reduce<1>(v); v[0] = v[0] * 1e-3; }
+    long long t2 = clock64();
+    if (T.leader()) { out[0] = t1 - t0; out[1] = t2 - t1; out[2] = (long long)v[0]; }
+}
+
+extern "C" int cpk_debug_barrier_cycles(int device, int iters, double *sync_cycles, double *reduce_cycles)
+{
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    long long *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 3 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(dc->ctl, 0, sizeof(TeamCtl), dc->stream));
+    void *params[] = {(void *)&dc->ctl, (void *)&dc->partials, (void *)&iters, (void *)&d_out};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_barrier_bench, dim3(dc->grid_blocks), dim3(kBlock), params, 0, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    long long h[3];
+    CUDA_TRY(cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    if (sync_cycles) *sync_cycles = (double)h[0] / iters;
+    if (reduce_cycles) *reduce_cycles = (double)h[1] / iters;
+    return CPK_OK;
 }
 
 // ===========================================================================
@@ -1157,10 +1186,8 @@ static int run_matvec(int device, const DevSell &A, const double *x, double *y, 
     }
     CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
     const bool grid = use_grid(A.nrows);
-    static const int ring_el = [] { const char *e = getenv("CPK_RING"); return e ? atoi(e) / 32 * 32 : 256; }();
-    const size_t rbytes = (size_t)kWarpsPerCta * kRingStages * 12 * ring_el;
-    if (grid) k_matvec<true><<<dc->grid_blocks, kBlock, rbytes, dc->stream>>>(A, dx, dy, ring_el);
-    else      k_matvec<false><<<1, kBlock, rbytes, dc->stream>>>(A, dx, dy, ring_el);
+    if (grid) k_matvec<true><<<dc->grid_blocks, kBlock, 0, dc->stream>>>(A, dx, dy);
+    else      k_matvec<false><<<1, kBlock, 0, dc->stream>>>(A, dx, dy);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
@@ -1265,7 +1292,6 @@ struct Plan {
     long long gs;           // global scalar scratch doubles
     int wide_cols;
     int restart, mem;
-    int ring_off, ring_elems;
 };
 
 static int make_plan(int solver, const cpk_opts *o, Plan *p)
@@ -1300,16 +1326,7 @@ static int make_plan(int solver, const cpk_opts *o, Plan *p)
         default: return fail(CPK_ERR_ARG, "unknown solver id %d", solver);
     }
     p->nvec += 2;
-    p->dsm = (p->dsm + 127) & ~(size_t)127;
-    // per-warp bulk-copy rings behind the solver's scratch: as many entries per
-    // stage as fit (256 preferred), none if CPK_RING=0
-    static const int ring_pref = [] { const char *e = getenv("CPK_RING"); return e ? atoi(e) : 256; }();
-    p->ring_off = (int)p->dsm;
-    p->ring_elems = 0;
-    for (int el = ring_pref / 32 * 32; el >= 64; el -= 32) {
-        const size_t need = (size_t)kWarpsPerCta * kRingStages * 12 * el;
-        if (p->dsm + need <= 200 * 1024) { p->ring_elems = el; p->dsm += need; break; }
-    }
+    p->dsm = (p->dsm + 15) & ~(size_t)15;
     return CPK_OK;
 }
 
@@ -1366,7 +1383,6 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
     a.work = S->d_work; a.work_len = (long long)plan.nvec * N;
     a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
-    a.ring_off = plan.ring_off; a.ring_elems = plan.ring_elems;
     CUDA_TRY(cudaMemcpyAsync(S->d_args, &a, sizeof a, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = S->d_sys; const SolveArgs *pa = S->d_args;
@@ -1450,8 +1466,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
         a.work = S->d_work; a.work_len = (long long)plan.nvec * S->h.N;
         a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
-        a.ring_off = plan.ring_off; a.ring_elems = plan.ring_elems;
-        hargs[i] = a;
+            hargs[i] = a;
         CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     }
     DevSystem *d_sys = nullptr; SolveArgs *d_args = nullptr;

@@ -47,79 +47,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
             sb = (int)((long long)A.nslices * (T.gwarp + 1) / T.nwarps);
         }
     }
-    if (sa < sb && T.ring.base != nullptr) {
-        // ---- bulk-copy ring path: (val, col) of the span arrive in shared memory ----
-        WarpRing &R = T.ring;
-        const int SE = R.elems;                 // entries per stage
-        int s = sa;
-        const int ka = __ldg(&A.sptr[sa]);
-        const int kb = __ldg(&A.sptr[sb]);
-        int send = __ldg(&A.sptr[s + 1]);
-        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-        int row = __ldg(&A.rowmap[s * 32 + T.lane]);
-        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
-        double acc = 0.0;
-        const int nch = (kb - ka + SE - 1) / SE;
-        auto post = [&](int j) {                // lane 0: request chunk j into its stage
-            const unsigned st = (R.n + (unsigned)j) % kRingStages;
-            const int k0 = ka + j * SE;
-            const unsigned ne = (unsigned)min(SE, kb - k0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&R.bar[st], ne * 12u);
-            bulk_g2s(R.val(st), &A.val[k0], ne * 8u, &R.bar[st]);
-            bulk_g2s(R.col(st), &A.col[k0], ne * 4u, &R.bar[st]);
-        };
-        if (T.lane == 0)
-            for (int j = 0; j < kRingStages && j < nch; ++j) post(j);
-        for (int j = 0; j < nch; ++j) {
-            const unsigned use = R.n + (unsigned)j;
-            const unsigned st = use % kRingStages, par = (use / kRingStages) & 1u;
-            {
-                long long t0 = clock64();
-                unsigned spins = 0;
-                while (!mbar_try_wait(&R.bar[st], par)) {
-                    if ((++spins & 0x3ff) == 0 && clock64() - t0 > kWatchdogCycles) { T.set_abort(); break; }
-                }
-            }
-            const double *sv = R.val(st);
-            const int *sc = R.col(st);
-            const int k0 = ka + j * SE;
-            const int ne = min(SE, kb - k0);
-            for (int e0 = 0; e0 < ne; e0 += 256) {          // 8 entries per lane at a time
-                int cc[8]; double vv[8], xv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = e0 + 32 * u + T.lane;
-                    if (e < ne) { cc[u] = sc[e]; vv[u] = sv[e]; } else { cc[u] = -1; vv[u] = 0.0; }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) xv[u] = (cc[u] >= 0) ? x[cc[u]] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int kk0 = k0 + e0 + 32 * u;       // warp-uniform
-                    if (e0 + 32 * u < ne) {
-                        while (kk0 >= send) {               // slice s is complete (possibly empty ones follow)
-                            if (row >= 0) epi(row, acc);
-                            acc = 0.0; ++s;
-                            send = send2; row = row2;
-                            send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-                            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
-                        }
-                        acc += vv[u] * xv[u];
-                    }
-                }
-            }
-            __syncwarp();
-            if (T.lane == 0 && j + kRingStages < nch) post(j + kRingStages);
-        }
-        R.n += (unsigned)nch;
-        while (s < sb) {
-            if (row >= 0) epi(row, acc);
-            acc = 0.0; ++s;
-            row = row2;
-            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
-        }
-    } else if (sa < sb) {
+    if (sa < sb) {
         int s = sa;
         int k = __ldg(&A.sptr[sa]);
         const int kb = __ldg(&A.sptr[sb]);

@@ -99,23 +99,32 @@ __device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
         ++itn;
         const double pAp_qCq = c.spmv_dot(PQ, APCQ);                // :151-152
         const double alpha = rn2 / pAp_qCq;                         // :154
-        TEAM_FOR(T, i, N) {                                         // :161-164
-            X[i] = X[i] + alpha * PQ[i];
-            GW[i] = GW[i] + alpha * APCQ[i];
+        {                                                           // :161-164
+            const double *const src[4] = {X, PQ, GW, APCQ};
+            team_map<4>(T, N, src, [&](int i, const double (&v)[4]) {
+                X[i] = v[0] + alpha * v[1];
+                GW[i] = v[2] + alpha * v[3];
+            });
         }
         T.sync();
         c.apply(GW, false, RU);                                     // :166
         part[0] = 0.0;
-        TEAM_FOR(T, i, N) {                                         // :167-168
-            if (i < n) part[0] += GW[i] * RU[i];
-            else { const double t = X[i] + RU[i]; part[0] += t * GW[i]; }
+        {                                                           // :167-168
+            const double *const src[3] = {GW, RU, X};
+            team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
+                if (i < n) part[0] += v[0] * v[1];
+                else { const double t = v[2] + v[1]; part[0] += t * v[0]; }
+            });
         }
         T.template reduce<1>(part);
         const double rn2_new = part[0];
         const double beta = rn2_new / rn2;                          // :169
-        TEAM_FOR(T, i, N) {                                         // :171-172
-            const double t = (i < n) ? RU[i] : X[i] + RU[i];
-            PQ[i] = -t + beta * PQ[i];
+        {                                                           // :171-172
+            const double *const src[3] = {RU, PQ, X};
+            team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
+                const double t = (i < n) ? v[0] : v[2] + v[0];
+                PQ[i] = -t + beta * v[1];
+            });
         }
         rn2 = rn2_new;
         if (rn2 < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)itn, rn2); break; }
@@ -799,15 +808,14 @@ k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *parti
         for (int i = threadIdx.x; i < (int)(sizeof(SolveArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    char *ring = s_args.ring_elems > 0 ? reinterpret_cast<char *>(g_dsm) + s_args.ring_off : nullptr;
     if (GRID) {
         GridTeam T;
-        T.init(ctl, partials, &sh, ring, s_args.ring_elems);
+        T.init(ctl, partials, &sh);
         T.wide = wide; T.wide_cols = wide_cols;
         solve_entry<SOLVER>(T, s_sys, s_args, g_dsm);
     } else {
         CtaTeam T;
-        T.init(ctl + blockIdx.x, nullptr, &sh, ring, s_args.ring_elems);
+        T.init(ctl + blockIdx.x, nullptr, &sh);
         solve_entry<SOLVER>(T, s_sys, s_args, g_dsm);
     }
 }

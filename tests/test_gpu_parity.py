@@ -87,6 +87,25 @@ def test_exprog2_nonsymmetric(cp, meth, extra, kind, team):
     _compare(cp, s, fac, meth, dict(EX_OPTS, **extra), team)
 
 
+@pytest.mark.parametrize("team", ["cta", "grid"])
+@pytest.mark.parametrize("env", [{"CPK_LDL_SYNCFREE": "1"}, {"CPK_LDL_NO_SHORTCUTS": "1"}, {"CPK_LDL_NO_TAIL": "1"},
+                                 {"CPK_LDL_SYNCFREE": "1", "CPK_LDL_NO_TAIL": "1"}])
+def test_ldl_walk_variants_agree(cp, env, team):
+    """The LDL' solve has two walks (level-synchronous, sync-free/tagged) and setup
+    shortcuts (trivial/fused rows, tail inversion); every combination must give the
+    oracle's answer (the switches are read when the operator is created)."""
+    s = load_system("cvxqp1_m")
+    fac = load_factors("cvxqp1_m", "superlu")
+    os.environ.update(env)
+    try:
+        _compare(cp, s, fac, "cpminres", dict(EX_OPTS), team)
+        s2 = load_system("cvxqp2_s")
+        _compare(cp, s2, load_factors("cvxqp2_s", "densebk"), "cpgmres", dict(EX_OPTS, restart=100), team)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+
+
 def test_exprog1_dense_bk_2x2_pivots(cp):
     from cpkrylov_b200.ldl import ldl_dense_bk
     s = load_system("cvxqp1_m")
