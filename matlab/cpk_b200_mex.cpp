@@ -1,0 +1,130 @@
+// cpk_b200_mex.cpp -- thin MEX gateway from MATLAB to libcpk_b200.so.
+//
+// NOT compiled in this repository's CI (no MATLAB / mex.h in the build image); it
+// is the reference-side binding a maintainer builds with
+//     mex -R2018a -I../include cpk_b200_mex.cpp -L../cpkrylov_b200 -lcpk_b200
+// Every branch is a mechanical translation mxArray <-> the plain-pointer C ABI of
+// include/cpk_b200.h; no arithmetic happens here.
+//
+//   h  = cpk_b200_mex('ldl2_create', G, B, C22, L, D, P)     opLDL2(A,B,C) ctor, ops/opLDL2.m:60-92
+//        cpk_b200_mex('ldl2_set', h, name, value)             public properties, opLDL2.m:45-50
+//   y  = cpk_b200_mex('ldl2_apply', h, z)                     M*z, opLDL2.m:161-188
+//   y  = cpk_b200_mex('ldl2_matvec', h, b)                    M\b, opLDL2.m:193-195
+//   s  = cpk_b200_mex('system_create', A, C, h)               (A, C, M) of method(b1,A,C,M,opts)
+//   [x, niters, solved, status, hist] = cpk_b200_mex('reg_solve', s, solver_id, b, optsvec)
+//        cpk_b200_mex('destroy', h)
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "cpk_b200.h"
+
+static void fail_if(int rc)
+{
+    if (rc == CPK_OK) return;
+    char msg[1024];
+    cpk_last_error(msg, sizeof msg);
+    const char *id = "cpk_b200:error";
+    if (rc == CPK_ERR_INDEFINITE && std::strstr(msg, "second-order")) id = "CPCGLanczos:IndefiniteError";  // cpcglanczos.m:161
+    mexErrMsgIdAndTxt(id, "%s", msg);
+}
+
+// MATLAB sparse (mwIndex == 64-bit with -R2018a / -largeArrayDims) -> cpk_csc
+static cpk_csc as_csc(const mxArray *a, std::vector<int64_t> &jc, std::vector<int64_t> &ir)
+{
+    if (!mxIsSparse(a) || !mxIsDouble(a) || mxIsComplex(a))
+        mexErrMsgIdAndTxt("cpk_b200:arg", "expected a real sparse double matrix");
+    const mwIndex *Jc = mxGetJc(a), *Ir = mxGetIr(a);
+    const size_t n = mxGetN(a), nnz = Jc[n];
+    jc.assign(Jc, Jc + n + 1);
+    ir.assign(Ir, Ir + nnz);
+    cpk_csc c;
+    c.nrows = (int64_t)mxGetM(a); c.ncols = (int64_t)n;
+    c.colptr = jc.data(); c.rowind = ir.data(); c.val = mxGetDoubles(a);
+    return c;
+}
+
+static cpk_handle as_handle(const mxArray *a) { return (cpk_handle)mxGetScalar(a); }
+
+static void at_exit(void) { cpk_destroy_all(); }
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("cpk_b200:arg", "first argument must be a command string");
+    mexAtExit(at_exit);
+    char cmdbuf[64];
+    mxGetString(prhs[0], cmdbuf, sizeof cmdbuf);
+    const std::string cmd(cmdbuf);
+
+    if (cmd == "ldl2_create") {                                   // G, B, C22, L, D, P
+        if (nrhs != 7) mexErrMsgIdAndTxt("cpk_b200:arg", "Invalid number of arguments.");   // opLDL2.m:61-63
+        std::vector<int64_t> jc[5], ir[5];
+        cpk_csc m[5];
+        for (int i = 0; i < 5; ++i) m[i] = as_csc(prhs[1 + i], jc[i], ir[i]);
+        // P is the sparse permutation MATRIX of [L,D,P] = ldl(K): column k has its 1 in row perm[k]
+        const mwIndex *Pjc = mxGetJc(prhs[6]), *Pir = mxGetIr(prhs[6]);
+        const size_t N = mxGetN(prhs[6]);
+        std::vector<int64_t> perm(N);
+        for (size_t k = 0; k < N; ++k) perm[k] = (int64_t)Pir[Pjc[k]];
+        cpk_handle h = 0;
+        fail_if(cpk_ldl2_create(&h, &m[0], &m[1], &m[2], &m[3], &m[4], perm.data(), 0));
+        plhs[0] = mxCreateDoubleScalar((double)h);
+    } else if (cmd == "ldl2_set") {                               // h, name, value
+        char name[32];
+        mxGetString(prhs[2], name, sizeof name);
+        const double v = mxGetScalar(prhs[3]);
+        const cpk_handle h = as_handle(prhs[1]);
+        if (!std::strcmp(name, "nitref")) fail_if(cpk_ldl2_set_nitref(h, v));
+        else if (!std::strcmp(name, "itref_tol")) fail_if(cpk_ldl2_set_itref_tol(h, v));
+        else if (!std::strcmp(name, "force_itref")) fail_if(cpk_ldl2_set_force_itref(h, (int)v));
+        else if (!std::strcmp(name, "residual_update")) fail_if(cpk_ldl2_set_residual_update(h, (int)v));
+        else if (!std::strcmp(name, "ru_stateful")) fail_if(cpk_ldl2_set_ru_stateful(h, (int)v));
+        else mexErrMsgIdAndTxt("cpk_b200:arg", "unknown opLDL2 property %s", name);
+    } else if (cmd == "ldl2_apply" || cmd == "ldl2_matvec") {     // h, z
+        const cpk_handle h = as_handle(prhs[1]);
+        int64_t N = 0;
+        fail_if(cpk_ldl2_size(h, &N, nullptr, nullptr));
+        if ((int64_t)mxGetNumberOfElements(prhs[2]) != N) mexErrMsgIdAndTxt("cpk_b200:arg", "vector length must be %lld", (long long)N);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
+        cpk_stats st;
+        if (cmd == "ldl2_apply") fail_if(cpk_ldl2_apply(h, mxGetDoubles(prhs[2]), mxGetDoubles(plhs[0]), CPK_MEM_HOST, &st));
+        else fail_if(cpk_ldl2_matvec(h, mxGetDoubles(prhs[2]), mxGetDoubles(plhs[0]), CPK_MEM_HOST, &st));
+    } else if (cmd == "system_create") {                          // A, C, h
+        std::vector<int64_t> jc[2], ir[2];
+        cpk_csc a = as_csc(prhs[1], jc[0], ir[0]), c = as_csc(prhs[2], jc[1], ir[1]);
+        cpk_handle s = 0;
+        fail_if(cpk_system_create(&s, &a, &c, as_handle(prhs[3])));
+        plhs[0] = mxCreateDoubleScalar((double)s);
+    } else if (cmd == "reg_solve") {                              // s, solver_id, b, [atol rtol btol itmax restart mem] (NaN = absent)
+        const cpk_handle s = as_handle(prhs[1]);
+        const int solver = (int)mxGetScalar(prhs[2]);
+        const size_t N = mxGetNumberOfElements(prhs[3]);
+        const double *ov = mxGetDoubles(prhs[4]);
+        const double *nm = mxGetDoubles(prhs[5]);                 // [n m]
+        cpk_opts o;
+        cpk_opts_default(&o, solver, (int64_t)nm[0], (int64_t)nm[1]);
+        if (!mxIsNaN(ov[0])) o.atol = ov[0];
+        if (!mxIsNaN(ov[1])) o.rtol = ov[1];
+        if (!mxIsNaN(ov[2])) o.btol = ov[2];
+        if (!mxIsNaN(ov[3])) o.itmax = (int64_t)ov[3];
+        if (!mxIsNaN(ov[4])) o.restart = (int32_t)ov[4];
+        if (!mxIsNaN(ov[5])) o.mem = (int32_t)ov[5];
+        const int64_t cap = cpk_hist_capacity(solver, &o);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
+        mxArray *hist = mxCreateDoubleMatrix((mwSize)cap, 3, mxREAL);     // column-major: 3 rows of the ABI = 3 columns here
+        cpk_stats st;
+        const int rc = cpk_reg_solve(s, solver, mxGetDoubles(prhs[3]), &o, mxGetDoubles(plhs[0]), CPK_MEM_HOST,
+                                     &st, mxGetDoubles(hist), cap);
+        fail_if(rc);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)st.niters);
+        if (nlhs > 2) plhs[2] = mxCreateLogicalScalar(st.solved != 0);
+        if (nlhs > 3) plhs[3] = mxCreateDoubleScalar((double)st.status);
+        if (nlhs > 4) { mxSetM(hist, (mwSize)st.hist_len); plhs[4] = hist; } else mxDestroyArray(hist);
+        if (nlhs > 5) plhs[5] = mxCreateDoubleScalar(st.t_solve_ms * 1e-3);
+    } else if (cmd == "destroy") {
+        fail_if(cpk_destroy(as_handle(prhs[1])));
+    } else {
+        mexErrMsgIdAndTxt("cpk_b200:arg", "unknown command %s", cmd.c_str());
+    }
+}

@@ -1,0 +1,50 @@
+function [x, stats, flag] = reg_cpkrylov_gpu(method, b, A, B, C, G, opts)
+%REG_CPKRYLOV_GPU  Drop-in for reg_cpkrylov (same signature, reg_cpkrylov.m:1) that
+% runs the Krylov loop and every preconditioner apply on a B200 through
+% cpk_b200_mex / libcpk_b200.so.  Only the factorization stays on the host
+% (untimed setup, stats.ptime), exactly where the reference calls ldl (opLDL2.m:82).
+%
+% Limitation: A must be an explicit sparse matrix (the reference also accepts a
+% Spot operator, reg_cpkrylov.m:40; use opLDL2gpu + the original kernels for that).
+    if (nargin < 6)
+        error('reg_cpkrylov: not enough inputs');                 % reg_cpkrylov.m:122-125
+    end
+    if nargin < 7, opts = struct(); end
+    ids = struct('cpcg',0,'cpcglanczos',1,'cpminres',2,'cpsymmlq',3,'cpgmres',4,'cpdqgmres',5);
+    name = func2str(method);
+    if ~isfield(ids, name), error('reg_cpkrylov_gpu: unknown method %s', name); end
+
+    tstartp = tic;
+    n = size(A,1); m = size(B,1);
+    K = [G B'; B -C];
+    [L, D, P] = ldl(K);                                           % opLDL2.m:81-82 (HSL MA57)
+    hM = cpk_b200_mex('ldl2_create', sparse(G), sparse(B), sparse(-C), L, D, sparse(P));
+    hS = cpk_b200_mex('system_create', sparse(A), sparse(C), hM);
+    ptime = toc(tstartp);
+    cleanup = onCleanup(@() cpk_b200_mex('destroy', hS));
+
+    names = {'nitref','itref_tol','residual_update','force_itref'};   % reg_cpkrylov.m:135-148
+    for k = 1:numel(names)
+        if isfield(opts, names{k}), cpk_b200_mex('ldl2_set', hM, names{k}, double(opts.(names{k}))); end
+    end
+
+    tstarts = tic;
+    ov = nan(1,6); f = {'atol','rtol','btol','itmax','restart','mem'};
+    for k = 1:6
+        if isfield(opts, f{k}), ov(k) = double(opts.(f{k})); end
+    end
+    [x, niters, solved, status, hist] = cpk_b200_mex('reg_solve', hS, ids.(name), b(:), ov, [n m]);
+    stats.niters = niters;
+    if strcmp(name, 'cpsymmlq')                                   % cpsymmlq.m:363-366
+        stats.cgresidHistory = hist(:,1); stats.lqresidHistory = hist(:,2); stats.qrresidHistory = hist(:,3);
+    else
+        stats.residHistory = hist(:,1);
+    end
+    if strcmp(name, 'cpcglanczos')                                % cpcglanczos.m:312-324
+        txt = {'maximum number of iterations attained', 'residual small compared to initial residual', 'backward error small'};
+        stats.status = txt{status+1};
+    end
+    flag.solved = solved;
+    stats.ptime = ptime;                                          % reg_cpkrylov.m:177-178
+    stats.stime = toc(tstarts);
+end
