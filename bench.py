@@ -180,6 +180,69 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_batch(args, rank, local_rank, world):
+    """BASELINE cfg 5: a batch of independent IPM-like KKT systems (pattern of the
+    reference's cvxqp1 example), block-partitioned over the ranks; every rank solves
+    its share in ONE launch (one CTA per system).  Not the headline line -- run with
+    --workload ipm_batch."""
+    import torch
+    import torch.distributed as dist
+    from cpkrylov_b200 import synth
+    from cpkrylov_b200.batch import BatchSolver, partition
+    from cpkrylov_b200.ldl import ldl_superlu
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    base = synth.load_cvxqp1()
+    lo, hi = partition(args.batch, world, rank)
+    opts = dict(atol=1e-6, rtol=1e-6, itmax=500, residual_update=True, nitref=1, force_itref=True)
+    t0 = time.perf_counter()
+    systems = [synth.ipm_batch_system(base, j) for j in range(lo, hi)]
+    facs = [ldl_superlu(synth.kp_matrix(w)) for w in systems]
+    bs = BatchSolver(systems, facs, opts, device=local_rank)
+    t_setup = time.perf_counter() - t0
+    rhs = [w["rhs"] for w in systems]
+    for _ in range(max(args.warmup, 3)):
+        bs.solve("cpminres", rhs, opts)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    iters = 0
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        xs, st = bs.solve("cpminres", rhs, opts)
+        iters += sum(d["niters"] for d in st)
+        dev_ms += bs.last_ms
+        if world > 1:
+            red = torch.tensor([min(int(d["solved"]) for d in st)], device="cuda")
+            dist.all_reduce(red, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t1
+    tt = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(iters)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        wall_max, dev_max = tt.tolist()
+        print(json.dumps({
+            "metric": "krylov_iterations_per_second", "value": cnt.item() / wall_max, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ipm_batch", "systems": args.batch, "n": base["n"], "m": base["m"], "solver": "cpminres",
+                       "opts": opts, "systems_per_rank": hi - lo, "device_ms_per_step": dev_max / args.steps,
+                       "setup_s": t_setup, "note": "end to end through the host-pointer batch ABI (H2D rhs, D2H solutions inside the timed region)"},
+            "e2e": {"value": cnt.item() / wall_max, "unit": "iterations/s",
+                    "h2d_bytes_per_step": 8 * base["N"] * (hi - lo), "d2h_bytes_per_step": 8 * base["N"] * (hi - lo)},
+            "gpu_launches": args.steps}))
+    bs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +260,7 @@ def main():
     ap.add_argument("--cpu-baseline-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="collect per-phase cycle shares (slower)")
+    ap.add_argument("--batch", type=int, default=256, help="systems in the ipm_batch workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -206,6 +270,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "ipm_batch":
+        run_batch(args, rank, local_rank, world)
         return
 
     import torch
@@ -254,11 +321,18 @@ def main():
                                    ct.byref(st), hist.ctypes.data, cap))
         return st
 
+    red_pin = torch.zeros(2, dtype=torch.int64).pin_memory()
+
     def step_collective(st):
+        # global convergence reduction of the step (the only collective of the path).
+        # It is completed before the next solve is launched: the persistent solver
+        # kernel owns every SM (1 CTA/SM, all registers), so an NCCL kernel still
+        # queued behind it would wait for the whole next solve.
         if world > 1:
-            red[0] = int(st.solved); red[1] = int(st.niters)
-            dist.all_reduce(red[0:1], op=dist.ReduceOp.MIN)
-            dist.all_reduce(red[1:2], op=dist.ReduceOp.SUM)
+            red_pin[0] = -int(st.solved); red_pin[1] = int(st.niters)      # MAX of -solved = -MIN(solved)
+            red.copy_(red_pin, non_blocking=True)
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            torch.cuda.current_stream().synchronize()
 
     def barrier():
         if world > 1:
@@ -308,6 +382,12 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    per_rank = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
+    mine = torch.tensor([wall_ms, dev_ms, 1e3 * (t3 - t2)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
     wall_ms_max, dev_ms_max, e2e_ms_max = [float(v) for v in tt.tolist()]
     tot_iters, tot_e2e_iters = [float(v) for v in cnt.tolist()]
 
@@ -335,7 +415,8 @@ def main():
                            l2_policy="working set (%.0f MB of matrices + vectors) exceeds the 126 MB L2; no explicit flush"
                                      % ((parts["B_spmv_H"] + parts["B_ldl"] + parts["B_resid"]) / 1e6 + 8 * N * 8 / 1e6),
                            setup_s=t_setup, t_factor_s=M.t_factor, t_upload_s=M.t_upload,
-                           ldl=info, device_ms_per_step=dev_ms_max / args.steps),
+                           ldl=info, device_ms_per_step=dev_ms_max / args.steps,
+                           device_ms_per_step_by_rank=[float(t[1]) / args.steps for t in per_rank]),
             "e2e": {"value": tot_e2e_iters / (e2e_ms_max * 1e-3), "unit": "iterations/s",
                     "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N + 8 * int(stats_last["hist_len"]) + 160},
             "gpu_launches": int(launches),
