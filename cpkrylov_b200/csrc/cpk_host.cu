@@ -679,6 +679,13 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
         T.sync();
         return;
     }
+    if (!GRID && M.track_rnorm == 2) {
+        CtaTeam T; T.init(ctl, nullptr, &sh);
+        PhaseClock dbg; dbg.start(T.leader(), st->phase_cycles);
+        ldl_solve_levels(T, M, in, y, false, &dbg);
+        T.sync();
+        return;
+    }
     if (GRID) {
         GridTeam T; T.init(ctl, partials, &sh);
         ldl2_apply(T, M, in, y, epoch, st, pc);
@@ -857,7 +864,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // triangular tail block, built row by row), so the whole tail becomes ONE
     // level that depends only on earlier levels and on the input vector.
     // Skipped when the substitution would fill in or grow too much.
-    static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 262144LL; }();
+    static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
     auto choose_cut = [&](const std::vector<int> &lev, const std::vector<char> &skip, int &maxlev) {
@@ -866,7 +873,8 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         maxlev = (int)cnt.size() - 1;
         long long tail = 0;
         int cut = maxlev + 1;
-        for (int l = maxlev; l >= 1; --l) { if (tail + cnt[l] > tail_rows_max) break; tail += cnt[l]; cut = l; }
+        static const int lmin = (getenv("CPK_LDL_CUT0") && atoi(getenv("CPK_LDL_CUT0")) == 0) ? 1 : 0;
+        for (int l = maxlev; l >= lmin; --l) { if (tail + cnt[l] > tail_rows_max) break; tail += cnt[l]; cut = l; }
         return cut;
     };
     auto add_to = [](std::vector<std::pair<int, double>> &acc, int code, double v) { acc.emplace_back(code, v); };

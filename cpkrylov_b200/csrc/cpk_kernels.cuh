@@ -400,10 +400,64 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                     }
                 }
             } else {
-                for (int q = 0; q < nb; ++q) {
-                    ItemMeta m; ItemChunk r;
-                    item_load(S, t + q, T.lane, m, r);
-                    item_process<false>(T, M, in, out, accumulate, 0ull, m, r);
+                // batch of warp-rows (one long row per item, <= 64 entries, 1x1 pivot): same
+                // three round trips for the whole batch, one butterfly per row
+                bool wr = true;
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    const int f0 = __shfl_sync(FULL, flg[q], 0);
+                    wr = wr && (q >= nb || ((f0 & F_WARPROW) && !(f0 & F_PARTNER) && wid[q] <= 64));
+                }
+                if (wr) {
+                    int rid0[B], pidx0[B], flg0[B];
+                    double d0[B];
+#pragma unroll
+                    for (int q = 0; q < B; ++q) {
+                        rid0[q] = __shfl_sync(FULL, rid[q], 0); pidx0[q] = __shfl_sync(FULL, pidx[q], 0);
+                        flg0[q] = __shfl_sync(FULL, flg[q], 0); d0[q] = __shfl_sync(FULL, dd[q], 0);
+                        c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
+                        if (q < nb && wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + T.lane]); v0[q] = __ldg(&S.val[beg[q] + T.lane]); }
+                        if (q < nb && wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + T.lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + T.lane]); }
+                    }
+                    double base[B], x0[B], x1[B];
+#pragma unroll
+                    for (int q = 0; q < B; ++q) {
+                        base[q] = 0.0; x0[q] = 0.0; x1[q] = 0.0;
+                        if (q < nb) {
+                            const bool isfwd = (flg0[q] & F_FWD) != 0;
+                            if (T.lane == 0) base[q] = (isfwd || (flg0[q] & F_WDIRECT)) ? in(pidx0[q]) : M.wv[rid0[q]];
+                            const double *depv = isfwd ? M.wv : M.yv;
+                            if (c0[q] >= 0) x0[q] = (c0[q] >= Nn) ? M.wv[c0[q] - Nn] : depv[c0[q]];
+                            else if (c0[q] <= -2) x0[q] = in(-c0[q] - 2);
+                            if (c1[q] >= 0) x1[q] = (c1[q] >= Nn) ? M.wv[c1[q] - Nn] : depv[c1[q]];
+                            else if (c1[q] <= -2) x1[q] = in(-c1[q] - 2);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < B; ++q) {
+                        double sum = 0.0;
+                        if (c0[q] != -1) sum -= v0[q] * x0[q];
+                        if (c1[q] != -1) sum -= v1[q] * x1[q];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+                        if (q < nb && T.lane == 0) {
+                            const bool isfwd = (flg0[q] & F_FWD) != 0;
+                            double acc = isfwd ? base[q] : base[q] / d0[q];
+                            acc += sum;
+                            if (isfwd && !(flg0[q] & F_FUSED)) M.wv[rid0[q]] = acc;
+                            else {
+                                if (isfwd) acc = acc / d0[q];
+                                if (isfwd || (flg0[q] & F_STORE)) M.yv[rid0[q]] = acc;
+                                if (accumulate) out[pidx0[q]] = out[pidx0[q]] + acc; else out[pidx0[q]] = acc;
+                            }
+                        }
+                    }
+                } else {
+                    for (int q = 0; q < nb; ++q) {
+                        ItemMeta m; ItemChunk r;
+                        item_load(S, t + q, T.lane, m, r);
+                        item_process<false>(T, M, in, out, accumulate, 0ull, m, r);
+                    }
                 }
             }
             t += nb;
