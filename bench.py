@@ -53,14 +53,23 @@ def algorithmic_bytes(s, info, solver, gpu_stats, mem=0, restart=0):
     B_resid = spmv(nnz_KP, N, N) + 8 * N
     B_ldl = 24 * info["nnz_L_off"] + 48 * N
     it = gpu_stats["niters"]
+    # N-vector passes of the Krylov algebra over the whole solve
     if solver in V_S:
-        vs = V_S[solver]
-    elif solver == "cpdqgmres":
-        vs = 3 * mem + 10
-    else:
-        vs = restart + 6          # cpgmres: mean of 2k+6 over a cycle
-    per_iter = B_H + B_C + 8 * N * vs
-    total = it * per_iter + gpu_stats["nldlsolve"] * B_ldl + gpu_stats["nresid"] * B_resid
+        vs_total = V_S[solver] * it
+    elif solver == "cpdqgmres":             # 2p + p' + 10 with the window actually filled at iteration k
+        vs_total = sum(2 * min(k, mem) + min(k - 1, mem) + 10 for k in range(1, it + 1))
+    else:                                   # cpgmres: 2k+6 at inner iteration k, k+2 at the end of a cycle
+        vs_total, k = 0, 0
+        for _ in range(it):
+            k += 1
+            vs_total += 2 * k + 6
+            if k == restart:
+                vs_total += k + 2; k = 0
+        if k:
+            vs_total += k + 2
+    vs = vs_total / max(it, 1)
+    per_iter = B_H + B_C
+    total = it * per_iter + 8 * N * vs_total + gpu_stats["nldlsolve"] * B_ldl + gpu_stats["nresid"] * B_resid
     parts = dict(B_spmv_H=B_H, B_spmv_C=B_C, B_ldl=B_ldl, B_resid=B_resid, B_vec=8 * N * vs)
     return total, parts
 
