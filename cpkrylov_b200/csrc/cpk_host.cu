@@ -686,6 +686,13 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
         T.sync();
         return;
     }
+    if (!GRID && M.track_rnorm == 2) {
+        CtaTeam T; T.init(ctl, nullptr, &sh);
+        PhaseClock dbg; dbg.start(T.leader(), st->phase_cycles);
+        ldl_solve_levels(T, M, in, y, false, &dbg);
+        T.sync();
+        return;
+    }
     if (GRID) {
         GridTeam T; T.init(ctl, partials, &sh);
         ldl2_apply(T, M, in, y, epoch, st, pc);
