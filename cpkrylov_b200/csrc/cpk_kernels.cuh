@@ -479,17 +479,25 @@ __device__ __forceinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn 
 }
 
 // r = xin - K*y with partial sums of r'r (and xin'xin): opLDL2.m:175-177,182-183
-template <class Team>
+struct NoRider {
+    static constexpr bool kActive = false;
+    __device__ __forceinline__ double operator()(int, double, double) const { return 0.0; }
+};
+
+// `rider(row, xin_row, y_row)` lets the caller piggy-back one more sum over the rows on
+// this pass (e.g. the P-inner product a solver needs right after the apply).
+template <class Team, class Rider>
 __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecIn xin, const double *y,
-                                            double *r, double &rr, double &xx, bool want_xx)
+                                            double *r, double &rr, double &xx, bool want_xx, Rider &rider, double &extra)
 {
-    rr = 0.0; xx = 0.0;
+    rr = 0.0; xx = 0.0; extra = 0.0;
     spmv_sell(T, M.KP, y, [&](int row, double s) {
         const double xi = xin(row);
         const double ri = xi - s;
         r[row] = ri;
         rr += ri * ri;
         if (want_xx) xx += xi * xi;
+        if (Rider::kActive) extra += rider(row, xi, y[row]);
     });
 }
 
@@ -498,10 +506,13 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
 // Entry: xin complete and visible to the team (caller synced).
 // Exit : y complete and visible (ends with a team barrier).
 // ---------------------------------------------------------------------------
-template <class Team>
-__device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xin, double *y, int &epoch,
-                           DevStatus *st, PhaseClock &pc)
+// Returns true when `*rider_sum` holds the rider's sum over the FINAL y (i.e. the
+// first residual pass was also the last touch of y); false otherwise.
+template <class Team, class Rider>
+__device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xin, double *y, int &epoch,
+                           DevStatus *st, PhaseClock &pc, Rider rider, double *rider_sum)
 {
+    bool rider_valid = false;
     const int n = M.nA;
     pc.mark(CPK_PH_VEC_);
     VecIn first = xin;
@@ -517,9 +528,11 @@ __device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
         pc.mark(CPK_PH_RESID_);
     }
     if (M.nitref > 0) {                                                 // :174
-        double red[2];
-        resid_phase(T, M, xin, y, M.rvec, red[0], red[1], true);
-        T.template reduce<2>(red);
+        double red[3];
+        resid_phase(T, M, xin, y, M.rvec, red[0], red[1], true, rider, red[2]);
+        if (Rider::kActive) T.template reduce<3>(red); else { double r2[2] = {red[0], red[1]}; T.template reduce<2>(r2); red[0] = r2[0]; red[1] = r2[1]; }
+        rider_valid = Rider::kActive;
+        if (rider_sum) *rider_sum = red[2];
         ++nres;
         pc.mark(CPK_PH_RESID_);
         double rNorm = sqrt(red[0]);
@@ -528,14 +541,16 @@ __device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
         bool rknown = true;
         while (nit < M.nitref && (rNorm >= M.itref_tol * xNorm || M.force_itref)) {   // :179
             VecIn rin{M.rvec, nullptr, n, false};
+            rider_valid = false;                                        // y changes: the rider's sum is stale
             ldl_solve(T, M, rin, y, true, ++epoch);                     // dy = LDL*r; y = y + dy
             T.sync();
             ++nsolve;
             ++nit;
             pc.mark(CPK_PH_LDL_);
             if (nit < M.nitref || M.track_rnorm) {
-                double r1[1], dummy;
-                resid_phase(T, M, xin, y, M.rvec, r1[0], dummy, false);
+                double r1[1], dummy, dummy2;
+                NoRider nr;
+                resid_phase(T, M, xin, y, M.rvec, r1[0], dummy, false, nr, dummy2);
                 T.template reduce<1>(r1);
                 rNorm = sqrt(r1[0]);
                 ++nres;
@@ -547,6 +562,14 @@ __device__ __noinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
         if (T.leader() && rknown) *M.rnorm_out = rNorm;
     }
     if (T.leader() && st) { st->napply += 1; st->nldlsolve += nsolve; st->nresid += nres; }
+    return rider_valid;
+}
+
+template <class Team>
+__device__ __forceinline__ void ldl2_apply(Team &T, const DevLdl &M, const VecIn xin, double *y, int &epoch,
+                                           DevStatus *st, PhaseClock &pc)
+{
+    ldl2_apply(T, M, xin, y, epoch, st, pc, NoRider(), (double *)nullptr);
 }
 
 }  // namespace cpk

@@ -45,6 +45,11 @@ struct Ctx {
         VecIn in{z, nullptr, n, neg_tail};
         ldl2_apply(T, S.M, in, y, epoch, st, pc);
     }
+    template <class Rider>
+    __device__ bool apply_with(const double *z, bool neg_tail, double *y, Rider rider, double *sum) {
+        VecIn in{z, nullptr, n, neg_tail};
+        return ldl2_apply(T, S.M, in, y, epoch, st, pc, rider, sum);
+    }
 };
 
 __device__ __forceinline__ double dsign(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0); }
@@ -72,6 +77,16 @@ __device__ __forceinline__ void sym_givens(double a, double b, double &c, double
         d = a / c;
     }
 }
+
+// g'r + t'w of cpcg.m:167-168 as a rider on the apply's residual pass: row < n
+// contributes g*r, row >= n contributes (a + u)*w  ([g;w] is the apply's input, [r;u] its output)
+struct CgRider {
+    static constexpr bool kActive = true;
+    const double *X; int n;
+    __device__ __forceinline__ double operator()(int row, double gw, double ru) const {
+        return (row < n) ? gw * ru : (X[row] + ru) * gw;
+    }
+};
 
 // ---------------------------------------------------------------------------
 // kernels/cpcg.m:118-193
@@ -107,16 +122,20 @@ __device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
             });
         }
         T.sync();
-        c.apply(GW, false, RU);                                     // :166
-        part[0] = 0.0;
-        {                                                           // :167-168
+        // :166-168.  g'r + t'w rides on the refinement-residual pass of the apply when that
+        // pass sees the final [r;u]; otherwise it is a pass of its own.
+        double rsum = 0.0;
+        const bool fused = c.apply_with(GW, false, RU, CgRider{X, n}, &rsum);
+        if (fused) part[0] = rsum;
+        else {
+            part[0] = 0.0;
             const double *const src[3] = {GW, RU, X};
             team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
                 if (i < n) part[0] += v[0] * v[1];
                 else { const double t = v[2] + v[1]; part[0] += t * v[0]; }
             });
+            T.template reduce<1>(part);
         }
-        T.template reduce<1>(part);
         const double rn2_new = part[0];
         const double beta = rn2_new / rn2;                          // :169
         {                                                           // :171-172
