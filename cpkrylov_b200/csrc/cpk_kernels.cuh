@@ -115,13 +115,20 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
 // sgn(i) = -1 for i >= nA when neg_tail (the solvers pass [u; -t], e.g.
 // cpminres.m:190); sub = [Aty; Cy] for the residual update (opLDL2.m:164-165).
 // ---------------------------------------------------------------------------
+// `add`/`scale`: the vector is z + scale*add evaluated on the fly (a solver's pending
+// axpy, e.g. g + alpha*Ap of cpcg.m:163-164, folded into the gather); `wb` asks the
+// apply to write the evaluated vector back into z during its residual pass.
 struct VecIn {
     const double *z;
     const double *sub;
     int nA;
     bool neg_tail;
+    const double *add = nullptr;
+    double scale = 0.0;
+    double *wb = nullptr;
     __device__ __forceinline__ double operator()(int i) const {
         double v = z[i];
+        if (add) v = v + scale * add[i];
         if (neg_tail && i >= nA) v = -v;
         if (sub) v = v - sub[i];
         return v;
@@ -493,6 +500,7 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
     rr = 0.0; xx = 0.0; extra = 0.0;
     spmv_sell(T, M.KP, y, [&](int row, double s) {
         const double xi = xin(row);
+        if (xin.wb) xin.wb[row] = xi;          // pending axpy of the caller lands in memory here
         const double ri = xi - s;
         r[row] = ri;
         rr += ri * ri;
@@ -509,10 +517,11 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
 // Returns true when `*rider_sum` holds the rider's sum over the FINAL y (i.e. the
 // first residual pass was also the last touch of y); false otherwise.
 template <class Team, class Rider>
-__device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xin, double *y, int &epoch,
+__device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xin0, double *y, int &epoch,
                            DevStatus *st, PhaseClock &pc, Rider rider, double *rider_sum)
 {
     bool rider_valid = false;
+    VecIn xin = xin0;
     const int n = M.nA;
     pc.mark(CPK_PH_VEC_);
     VecIn first = xin;
@@ -533,6 +542,7 @@ __device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
         if (Rider::kActive) T.template reduce<3>(red); else { double r2[2] = {red[0], red[1]}; T.template reduce<2>(r2); red[0] = r2[0]; red[1] = r2[1]; }
         rider_valid = Rider::kActive;
         if (rider_sum) *rider_sum = red[2];
+        if (xin.wb) { xin.add = nullptr; xin.wb = nullptr; }           // z now holds the evaluated vector
         ++nres;
         pc.mark(CPK_PH_RESID_);
         double rNorm = sqrt(red[0]);

@@ -46,8 +46,7 @@ struct Ctx {
         ldl2_apply(T, S.M, in, y, epoch, st, pc);
     }
     template <class Rider>
-    __device__ bool apply_with(const double *z, bool neg_tail, double *y, Rider rider, double *sum) {
-        VecIn in{z, nullptr, n, neg_tail};
+    __device__ bool apply_with(const VecIn &in, double *y, Rider rider, double *sum) {
         return ldl2_apply(T, S.M, in, y, epoch, st, pc, rider, sum);
     }
 };
@@ -82,9 +81,9 @@ __device__ __forceinline__ void sym_givens(double a, double b, double &c, double
 // contributes g*r, row >= n contributes (a + u)*w  ([g;w] is the apply's input, [r;u] its output)
 struct CgRider {
     static constexpr bool kActive = true;
-    const double *X; int n;
+    const double *X, *PQ; double alpha; int n;          // a = X + alpha*PQ is still pending (it lands in memory with the p,q update)
     __device__ __forceinline__ double operator()(int row, double gw, double ru) const {
-        return (row < n) ? gw * ru : (X[row] + ru) * gw;
+        return (row < n) ? gw * ru : ((X[row] + alpha * PQ[row]) + ru) * gw;
     }
 };
 
@@ -114,34 +113,38 @@ __device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
         ++itn;
         const double pAp_qCq = c.spmv_dot(PQ, APCQ);                // :151-152
         const double alpha = rn2 / pAp_qCq;                         // :154
-        {                                                           // :161-164
-            const double *const src[4] = {X, PQ, GW, APCQ};
-            team_map<4>(T, N, src, [&](int i, const double (&v)[4]) {
-                X[i] = v[0] + alpha * v[1];
-                GW[i] = v[2] + alpha * v[3];
-            });
+        // :161-164.  x,a += alpha*(p,q) is deferred to the p,q update below (same pass).
+        // g,w += alpha*(Ap,Cq): with refinement on, the apply evaluates it on the fly and
+        // stores it during its residual pass; otherwise it is a pass of its own.
+        VecIn in{GW, nullptr, n, false};
+        if (c.S.M.nitref > 0) { in.add = APCQ; in.scale = alpha; in.wb = GW; }
+        else {
+            const double *const src[2] = {GW, APCQ};
+            team_map<2>(T, N, src, [&](int i, const double (&v)[2]) { GW[i] = v[0] + alpha * v[1]; });
+            T.sync();
         }
-        T.sync();
         // :166-168.  g'r + t'w rides on the refinement-residual pass of the apply when that
         // pass sees the final [r;u]; otherwise it is a pass of its own.
         double rsum = 0.0;
-        const bool fused = c.apply_with(GW, false, RU, CgRider{X, n}, &rsum);
+        const bool fused = c.apply_with(in, RU, CgRider{X, PQ, alpha, n}, &rsum);
         if (fused) part[0] = rsum;
         else {
             part[0] = 0.0;
-            const double *const src[3] = {GW, RU, X};
-            team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
+            const double *const src[4] = {GW, RU, X, PQ};
+            team_map<4>(T, N, src, [&](int i, const double (&v)[4]) {
                 if (i < n) part[0] += v[0] * v[1];
-                else { const double t = v[2] + v[1]; part[0] += t * v[0]; }
+                else { const double t = (v[2] + alpha * v[3]) + v[1]; part[0] += t * v[0]; }
             });
             T.template reduce<1>(part);
         }
         const double rn2_new = part[0];
         const double beta = rn2_new / rn2;                          // :169
-        {                                                           // :171-172
+        {                                                           // :161-162 and :171-172
             const double *const src[3] = {RU, PQ, X};
             team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
-                const double t = (i < n) ? v[0] : v[2] + v[0];
+                const double xi = v[2] + alpha * v[1];
+                X[i] = xi;
+                const double t = (i < n) ? v[0] : xi + v[0];
                 PQ[i] = -t + beta * v[1];
             });
         }
