@@ -186,6 +186,28 @@ __device__ double lanczos_start(Ctx<Team> &c, const double *b, double *U, double
 // u = A vk, t = C qk, alpha, vprec = M[u;-t], unnormalised v_{k+1}, q_{k+1} and
 // beta^2 = u'v_{k+1} + t'q_{k+1}   (cpminres.m:187-194).  VKM1 == nullptr drops
 // the beta*v_{k-1} term (cpsymmlq.m:202-204).
+// The Lanczos three-term update and its trailing P-inner product as a rider on the
+// apply's residual pass (cpminres.m:191-194): row r of the pass sees the apply's input
+// xi = [u; -t]_r and output yi = vprec_r, writes v_{k+1} / q_{k+1} and returns u_r*v_r
+// (resp. t_r*q_r).  Association as in the reference: (vprec - alpha*vk) - beta*vkm1 and
+// ((qk - vprec) - alpha*qk) - beta*qkm1.
+struct LanczosRider {
+    static constexpr bool kActive = true;
+    const double *VK, *VKM1;        // VKM1 == nullptr: no beta term (cpsymmlq.m:202-204)
+    double *VKP1;
+    double alpha, beta;
+    int n;
+    __device__ __forceinline__ double operator()(int row, double xi, double yi) const {
+        const double vk = VK[row];
+        double v, u;
+        if (row < n) { u = xi; v = yi - alpha * vk; }
+        else { u = -xi; v = vk - yi; v = v - alpha * vk; }
+        if (VKM1) v = v - beta * VKM1[row];
+        VKP1[row] = v;
+        return u * v;
+    }
+};
+
 template <class Team>
 __device__ void lanczos_step(Ctx<Team> &c, const double *VK, const double *VKM1, double beta,
                              double *U, double *VPREC, double *VKP1, double &alpha, double &betasq)
@@ -193,7 +215,9 @@ __device__ void lanczos_step(Ctx<Team> &c, const double *VK, const double *VKM1,
     Team &T = c.T;
     const int n = c.n, N = c.N;
     alpha = c.spmv_dot(VK, U);
-    c.apply(U, true, VPREC);
+    double rsum = 0.0;
+    VecIn in{U, nullptr, n, true};
+    if (c.apply_with(in, VPREC, LanczosRider{VK, VKM1, VKP1, alpha, beta, n}, &rsum)) { betasq = rsum; return; }
     double part[1] = {0.0};
     if (VKM1) {
         TEAM_FOR(T, i, N) {
