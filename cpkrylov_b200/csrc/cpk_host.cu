@@ -367,7 +367,7 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
         deal_level(W, first_item, W.nitems - first_item, deal_warps);
     }
     // segments: a level with at least 2 items per warp is "bulk" (blocks of
-    // consecutive items per warp, prefetch pipeline); runs of smaller levels
+    // consecutive items per warp); runs of smaller levels
     // are merged into one chain segment dealt round-robin.
     int chain_first = -1, chain_end = -1;
     auto flush_chain = [&]() {

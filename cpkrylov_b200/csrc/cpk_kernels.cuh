@@ -1,7 +1,8 @@
 // cpk_kernels.cuh -- the phase functions of the hot path, written once against
 // the Team abstraction:
 //   spmv_sell      sparse mtimes  (cpcg.m:151-152, cpminres.m:187-188, opLDL2.m:175,182 ...)
-//   ldl_solve      P * L^-T * D^-1 * L^-1 * P'  as ONE sync-free sweep (opLDL2.m:86)
+//   ldl_solve      P * L^-T * D^-1 * L^-1 * P'  over one item list: level-synchronous walk
+//                  (default) or sync-free tagged walk (opLDL2.m:86)
 //   ldl2_apply     opLDL2.multiply (opLDL2.m:161-188)
 #pragma once
 #include "cpk_device.cuh"
@@ -23,8 +24,8 @@ struct PhaseClock {
 };
 
 // ---------------------------------------------------------------------------
-// SpMV, SELL-32: one warp per slice, one lane per row, entries of a row are
-// accumulated left to right (the order a CSR/CSC CPU kernel uses).  Matrix
+// SpMV, SELL-32: one lane per row, entries of a row are accumulated left to
+// right (the order a CSR/CSC CPU kernel uses).  Matrix
 // arrays are read-only for the kernel lifetime -> ld.global.nc; the vector x is
 // mutable across phases of the persistent kernel -> plain (coherent) loads.
 // Epi is called as epi(row, sum) by the lane that owns the row.
@@ -33,7 +34,7 @@ template <class Team, class Epi>
 __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
     // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
-    // range are one contiguous span, walked in chunks of 4 entries per lane with
+    // range are one contiguous span, walked in chunks of 8 entries per lane with
     // the next chunk's loads issued before the current chunk's x-gathers are
     // consumed (register double buffering), so HBM latency is off the per-slice
     // critical path.  Slice ends come from sptr, prefetched one slice ahead.
@@ -292,41 +293,6 @@ __device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const 
             }
         }
     }
-}
-
-// Level-synchronous walk of the same item list: one team barrier per dependency
-// level, plain 8-byte values, no polling.  Inside a level every warp streams a
-// contiguous range of items with the next item's row prefetched.  This is the
-// default: after the setup-time shortcuts (trivial / fused rows, tail inversion)
-// the sweeps of a KKT preconditioner have a handful of levels.
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// Pull the lines of item t into L2 ahead of use (no registers, no shared memory):
-// lane i fetches the i-th 128-byte line of the item's per-slot arrays / entries.
-__device__ __forceinline__ void item_prefetch(const DevSweep &S, int t, int lane)
-{
-    const int slot0 = t * 32;
-    const char *p = nullptr;
-    switch (lane) {
-        case 0: p = (const char *)&S.rid[slot0]; break;
-        case 1: p = (const char *)&S.pidx[slot0]; break;
-        case 2: p = (const char *)&S.flags[slot0]; break;
-        case 3: p = (const char *)&S.d[slot0]; break;
-        case 4: p = (const char *)&S.d[slot0 + 16]; break;
-        case 5: p = (const char *)&S.sptr[t]; break;
-        default: break;
-    }
-    if (p) prefetch_l2(p);
-}
-__device__ __forceinline__ void item_prefetch_entries(const DevSweep &S, int kbeg, int kend, int lane)
-{
-    // entries [kbeg, kend): col 4 B, val 8 B per entry -> one line per 32 / 16 entries
-    const int ncl = (kend - kbeg + 31) / 32, nvl = (kend - kbeg + 15) / 16;
-    if (lane < ncl) prefetch_l2(&S.col[kbeg + lane * 32]);
-    else if (lane - ncl < nvl) prefetch_l2(&S.val[kbeg + (lane - ncl) * 16]);
 }
 
 // Level-synchronous walk of the item list: one team barrier per dependency

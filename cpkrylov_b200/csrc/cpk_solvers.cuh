@@ -542,7 +542,6 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
     int *cols = (int *)(z + R);
     double *Hg = c.A.gs;                        // (R+1) x R
     __shared__ double s_resid;
-    __shared__ int s_err;
 
     TEAM_FOR(T, i, N) X[i] = 0.0;
     for (int j = threadIdx.x; j <= R; j += blockDim.x) cols[j] = j;
@@ -650,7 +649,6 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
         T.sync();
         c.pc.mark(CPK_PH_VEC_);
     }
-    (void)s_err;
     if (T.leader()) {
         c.st->niters = (outer > 0 ? (outer - 1) * R : 0) + k;       // :267
         c.st->hist_len = hl;
