@@ -257,6 +257,23 @@ def test_synthetic_lap3d_reduced_vs_oracle(cp, meth, extra):
     assert relerr(xg, w["xstar"]) < 1e-3
 
 
+def test_stress_deep_filled_factor(cp):
+    """SURVEY 8d 'stress' variant (k=6 entries per row of B in a 64-wide window) at reduced
+    size: L has fill and hundreds of dependency levels, rows of hundreds of entries; the grid
+    team then walks the sweep sync-free (chosen at setup from the depth)."""
+    from cpkrylov_b200 import synth
+    from cpkrylov_b200.ldl import ldl_superlu
+    w = synth.kkt_lap3d(g=24, k=6, window=64, seed_B=2)
+    s = dict(Q=w["H"], A=w["B"], C=w["C"], G=w["G"], rhs=w["rhs"], n=w["n"], m=w["m"], N=w["n"] + w["m"])
+    fac = ldl_superlu(synth.kp_matrix(w))
+    for team in ("grid", "cta"):
+        xg, sg, xo, so = _compare(cp, s, fac, "cpcg", dict(print=False), team)
+        assert relerr(xg, w["xstar"]) < 1e-3
+    M = cp.opLDL2(w["G"], w["B"], -w["C"], factors=fac)
+    assert M.info()["levels_fwd"] > 50
+    M.close()
+
+
 def test_full_size_properties_cfg3(cp):
     """BASELINE cfg 3 at full size (n = 10^6): size-independent properties instead
     of an oracle run -- operator identity, linearity of the apply, true residual
