@@ -81,9 +81,48 @@ struct DevSweep {
     const double *dp;       // partner's diagonal entry
 };
 
+// One-CTA walk of the LDL' solve ("compact walk", small systems): the sweep values
+// w and y live in SHARED memory and the factor is streamed through a shared-memory
+// ring by the bulk-copy engine, so the dependent chain of a level is a shared-memory
+// gather, a few flops and __syncthreads instead of three L2 round trips.  The
+// interpreter is kept to a handful of instructions per step, because one warp's
+// dependent instruction stream is what bounds a level.  The stream is a sequence of
+// fixed-size blocks:
+//   int4  {steps in the block, 0, 0, 0}
+//   int4  slot[steps][16]   what warp w does in step s:
+//           {data offset, kind | CW_BARRIER | width << 8 | stride << 24, z, 0}
+//           kind CW_ROWS2   : `stride` rows, one per lane, <= 2 entries each
+//                             data: per lane {int tgt, col0, col1, 0; double val0, val1}
+//           kind CW_ROWS    : `stride` rows, one per lane, `width` <= 8 entries each
+//                             data: int tgt[S]; double val[width][S]; int col[width][S]
+//           kind CW_WARPROW : one long row spread over the 32 lanes, z = target
+//                             data: double val[width][32]; int col[width][32]
+//           kind CW_DCHUNK  : rows z .. z+width-1 of D^-1 (width <= 512; stride = 1: the chunk has 2x2 blocks);
+//                             warp w takes rows 32w..32w+31 of the chunk
+//                             data: double d[n]; (double e[n]; double dp[n]; int partner[n])
+//           kind 0          : nothing
+//           CW_BARRIER (same in all 16 slots of a step): __syncthreads after the step
+//                             -- a dependency level ends
+// tgt/col index the shared vector sv[2N] (w = sv[0..N), y = sv[N..2N)), col -1 = padding.
+constexpr int kCwBlock = 16384;     // bytes per stream block
+constexpr int kCwStages = 3;        // ring depth
+constexpr int CW_ROWS2 = 1, CW_ROWS = 2, CW_WARPROW = 3, CW_DCHUNK = 4;
+constexpr int CW_BARRIER = 16;
+struct DevCompact {
+    int nblk;                       // 0: no stream was built
+    int smem_off;                   // byte offset of the walk's region in dynamic shared memory, < 0: walk off
+    const unsigned char *stream;    // [nblk * kCwBlock]
+    const int *perm;                // [N] w_i = z[perm_i]
+};
+__host__ __device__ inline size_t cw_smem_bytes(int N)
+{
+    return (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16 + (size_t)16 * N;
+}
+
 struct DevLdl {
     int N, nA, nC;
     DevSweep sw;
+    DevCompact cw;
     // sync-free state (row-id indexed): value + the epoch of the solve that
     // produced it, read and written as ONE 128-bit atomic access
     Tagged *wbuf, *ybuf;
@@ -143,6 +182,7 @@ struct SolveArgs {
     long long hist_cap;
     double *gs;             // GMRES/DQGMRES scalar scratch in global memory
     DevStatus *status;
+    int     cw_off;         // byte offset of the compact-walk region in dynamic shared memory, < 0: off
 };
 
 // ---------------------------------------------------------------------------
@@ -192,6 +232,28 @@ __device__ __forceinline__ int ld_volatile(const int *p) {
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+
+// shared-memory barrier + bulk copy (global -> shared) of the compact walk's ring
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// dynamic shared memory of the solver kernels: [solver scratch][compact-walk region]
+extern __shared__ double g_dsm[];
 
 // Team-shared control block in global memory (one per launch team).
 struct TeamCtl {

@@ -392,6 +392,207 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
 // ===========================================================================
 // device objects
 // ===========================================================================
+// ---------------------------------------------------------------------------
+// Stream builder of the compact (one-CTA) walk: see DevCompact in cpk_device.cuh.
+// A "step" is a set of items that may run concurrently and ends with a CTA
+// barrier; a dependency level is one step (plus one step per extra part of rows
+// too long for a single item).  Runs of one-item steps become CW_SEQ groups.
+// ---------------------------------------------------------------------------
+struct CwItemH {
+    int kind;                               // CW_ROWS / CW_WARPROW / CW_DCHUNK
+    int width, stride;                      // D chunk: count in `width`, has2x2 in `stride`
+    int z;                                  // warp-row: target; D chunk: first row
+    std::vector<unsigned char> data;        // multiple of 16 bytes
+};
+
+struct CwStream {
+    std::vector<unsigned char> bytes;       // finished blocks
+    int nblk = 0;
+    // block under construction
+    std::vector<int> table;                 // 4 ints per slot, kWarpsPerCta slots per step
+    std::vector<unsigned char> blob;
+    long long n_levels = 0, n_steps = 0, n_items = 0;
+    int rot = 0;                            // first warp of the next step (rotates, so that the warp
+                                            // busy in one step is rarely the one busy in the next)
+    size_t used(size_t more_steps, size_t more_bytes) const {
+        return 16 + 4 * table.size() + 16 * kWarpsPerCta * more_steps + blob.size() + more_bytes;
+    }
+    void flush() {
+        if (table.empty()) return;
+        const size_t nsteps = table.size() / (4 * kWarpsPerCta);
+        const size_t area = 16 + 4 * table.size();
+        std::vector<unsigned char> blk(kCwBlock, 0);
+        int *h = reinterpret_cast<int *>(blk.data());
+        h[0] = (int)nsteps;
+        int *dst = h + 4;
+        for (size_t i = 0; i < table.size(); i += 4) {
+            dst[i] = table[i] + ((table[i + 1] & 15) ? (int)area : 0);
+            dst[i + 1] = table[i + 1]; dst[i + 2] = table[i + 2]; dst[i + 3] = table[i + 3];
+        }
+        if (!blob.empty()) memcpy(blk.data() + area, blob.data(), blob.size());
+        bytes.insert(bytes.end(), blk.begin(), blk.end());
+        ++nblk;
+        table.clear(); blob.clear();
+    }
+    // appends one step (a row of kWarpsPerCta empty slots) and returns its first slot
+    size_t new_step() { table.resize(table.size() + 4 * kWarpsPerCta, 0); ++n_steps; return table.size() - 4 * kWarpsPerCta; }
+    void set_slot(size_t step0, int w, int off, const CwItemH &it) {
+        int *sl = &table[step0 + 4 * w];
+        sl[0] = off; sl[1] = it.kind | (it.width << 8) | (it.stride << 24); sl[2] = it.z;
+    }
+    int put_data(const CwItemH &it) {
+        const int off = (int)blob.size();
+        blob.insert(blob.end(), it.data.begin(), it.data.end());
+        ++n_items;
+        return off;
+    }
+    void barrier_after(size_t step0) { for (int w = 0; w < kWarpsPerCta; ++w) table[step0 + 4 * w + 1] |= CW_BARRIER; }
+    // One dependency level (or the D pass): its items run concurrently, a CTA barrier
+    // closes it.  More than kWarpsPerCta items take several steps, only the last has the barrier.
+    void level(const std::vector<CwItemH> &items) {
+        if (items.empty()) return;
+        ++n_levels;
+        if (items[0].kind == CW_DCHUNK) {
+            size_t st = 0;
+            for (auto &it : items) {        // a chunk is shared by all warps: warp w takes rows 32w .. 32w+31
+                if (used(1, it.data.size()) > (size_t)kCwBlock) flush();
+                st = new_step();
+                const int off = put_data(it);
+                for (int w = 0; w < kWarpsPerCta; ++w) if (32 * w < it.width) set_slot(st, w, off, it);
+            }
+            barrier_after(st);
+            return;
+        }
+        size_t i = 0, st = 0;
+        while (i < items.size()) {
+            if (used(1, items[i].data.size()) > (size_t)kCwBlock) flush();      // the level continues in the next block
+            st = new_step();
+            for (int q = 0; q < kWarpsPerCta && i < items.size(); ++q) {
+                if (used(0, items[i].data.size()) > (size_t)kCwBlock) break;
+                set_slot(st, (rot + q) % kWarpsPerCta, put_data(items[i]), items[i]);
+                ++i;
+            }
+            rot = (rot + 5) % kWarpsPerCta;
+        }
+        barrier_after(st);
+    }
+};
+
+static void cw_put(std::vector<unsigned char> &b, const void *src, size_t n)
+{
+    const unsigned char *s = static_cast<const unsigned char *>(src);
+    if (n) b.insert(b.end(), s, s + n);
+}
+
+// items of one sweep direction.  R.row(i) = dependency list of LDL row i as (row id, value);
+// `toff`/`coff`: offsets of the target and of the dependencies in the shared vector sv[2N].
+static void cw_sweep(CwStream &S, int N, const HCsr &R, const std::vector<int> &lev, int nlev, int toff, int coff)
+{
+    constexpr int kMaxWidth = 16;           // entries per lane in one item
+    std::vector<std::vector<int>> byLevel(nlev);
+    for (int i = 0; i < N; ++i) if (R.len(i) > 0) byLevel[lev[i]].push_back(i);
+    typedef std::vector<CwItemH> Items;
+    auto emit = [&](Items &&items) { S.level(items); };
+    for (int l = 0; l < nlev; ++l) {
+        std::vector<int> &rows = byLevel[l];
+        if (rows.empty()) continue;
+        std::stable_sort(rows.begin(), rows.end(), [&](int a, int b) { return R.len(a) < R.len(b); });
+        Items first;
+        std::vector<Items> later;           // later[j-1] = parts j of the long rows
+        size_t k = 0;
+        // short rows: up to 32 per item, one lane each
+        while (k < rows.size() && R.len(rows[k]) <= kLongRow) {
+            size_t k1 = k;
+            int width = 0;
+            while (k1 < rows.size() && k1 - k < 32 && R.len(rows[k1]) <= kLongRow) { width = std::max(width, R.len(rows[k1])); ++k1; }
+            const int stride = ((int)(k1 - k) + 3) & ~3;        // lanes stored (idle lanes of a thin item are not)
+            CwItemH it{width <= 2 ? CW_ROWS2 : CW_ROWS, width, stride, 0, {}};
+            if (width <= 2) {
+                // one 32-byte record per lane: {target, col0, col1, 0, val0, val1}
+                for (int q = 0; q < stride; ++q) {
+                    int rec_i[4] = {-1, -1, -1, 0};
+                    double rec_v[2] = {0.0, 0.0};
+                    if (k + q < k1) {
+                        const int r = rows[k + q];
+                        rec_i[0] = toff + r;
+                        for (int j = 0; j < R.len(r); ++j) { rec_i[1 + j] = coff + R.col[R.ptr[r] + j]; rec_v[j] = R.val[R.ptr[r] + j]; }
+                    }
+                    cw_put(it.data, rec_i, 16);
+                    cw_put(it.data, rec_v, 16);
+                }
+            } else {
+                int tgt[32];
+                for (int q = 0; q < 32; ++q) tgt[q] = (k + q < k1) ? toff + rows[k + q] : -1;
+                cw_put(it.data, tgt, (size_t)4 * stride);
+                std::vector<double> val((size_t)width * stride, 0.0);
+                std::vector<int> col((size_t)width * stride, -1);
+                for (size_t q = k; q < k1; ++q) {
+                    const int r = rows[q];
+                    for (int j = 0; j < R.len(r); ++j) {
+                        val[(size_t)j * stride + (q - k)] = R.val[R.ptr[r] + j];
+                        col[(size_t)j * stride + (q - k)] = coff + R.col[R.ptr[r] + j];
+                    }
+                }
+                cw_put(it.data, val.data(), val.size() * 8);
+                cw_put(it.data, col.data(), col.size() * 4);
+            }
+            first.push_back(std::move(it));
+            k = k1;
+        }
+        // long rows: the 32 lanes share the row, <= 32*kMaxWidth entries per part
+        for (; k < rows.size(); ++k) {
+            const int r = rows[k], len = R.len(r);
+            int part = 0;
+            for (int e0 = 0; e0 < len; e0 += 32 * kMaxWidth, ++part) {
+                const int cnt = std::min(len - e0, 32 * kMaxWidth);
+                const int width = (cnt + 31) / 32;
+                CwItemH it{CW_WARPROW, width, 32, toff + r, {}};
+                std::vector<double> val((size_t)width * 32, 0.0);
+                std::vector<int> col((size_t)width * 32, -1);
+                for (int j = 0; j < cnt; ++j) { val[j] = R.val[R.ptr[r] + e0 + j]; col[j] = coff + R.col[R.ptr[r] + e0 + j]; }
+                cw_put(it.data, val.data(), val.size() * 8);
+                cw_put(it.data, col.data(), col.size() * 4);
+                if (part == 0) first.push_back(std::move(it));
+                else {
+                    if ((int)later.size() < part) later.resize(part);
+                    later[part - 1].push_back(std::move(it));
+                }
+            }
+        }
+        emit(std::move(first));
+        for (auto &st : later) emit(std::move(st));
+    }
+}
+
+static void cw_dpass(CwStream &S, int N, const std::vector<double> &d, const std::vector<double> &e, const std::vector<int> &partner)
+{
+    std::vector<CwItemH> items;
+    for (int i0 = 0; i0 < N;) {
+        bool has2 = false;
+        int cnt = std::min(512, N - i0);
+        for (int r = 0; r < cnt; ++r) has2 = has2 || partner[i0 + r] >= 0;
+        if (has2) cnt = std::min(cnt, 256);
+        CwItemH it{CW_DCHUNK, cnt, has2 ? 1 : 0, i0, {}};
+        cw_put(it.data, &d[i0], (size_t)cnt * 8);
+        if (has2) {
+            std::vector<double> ee(cnt, 0.0), dp(cnt, 1.0);
+            std::vector<int> pr(cnt, -1);
+            for (int r = 0; r < cnt; ++r) {
+                const int i = i0 + r, q = partner[i];
+                if (q < 0) continue;
+                pr[r] = q; dp[r] = d[q]; ee[r] = e[std::min(i, q)];
+            }
+            cw_put(it.data, ee.data(), (size_t)cnt * 8);
+            cw_put(it.data, dp.data(), (size_t)cnt * 8);
+            cw_put(it.data, pr.data(), (size_t)cnt * 4);
+        }
+        while (it.data.size() % 16) it.data.push_back(0);
+        items.push_back(std::move(it));
+        i0 += cnt;
+    }
+    S.level(items);
+}
+
 struct DevArena {
     std::vector<void *> ptrs;
     int device = 0;
@@ -509,6 +710,7 @@ struct DeviceCtx {
     int wide_cols = 0;
     DevStatus *h_status = nullptr;  // pinned
     int h_status_cap = 0;
+    int max_dsm = 0;                // dynamic shared memory every solver / apply kernel may ask for
 };
 constexpr int kMaxBatch = 4096;
 static std::mutex g_mu;
@@ -566,7 +768,7 @@ static const void *solver_kernel(int solver, bool grid)
     return nullptr;
 }
 template <bool GRID> __global__ void k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st,
-                                             TeamCtl *ctl, double *partials);
+                                             TeamCtl *ctl, double *partials, int cw_off);
 template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y);
 
 static int get_device_ctx(int device, DeviceCtx **out)
@@ -592,10 +794,17 @@ static int get_device_ctx(int device, DeviceCtx **out)
     if (!coop) return fail(CPK_ERR_CUDA, "device does not support cooperative launch");
     // allow the largest dynamic shared memory the solver kernels may ask for
     int per_sm = 1;
-    for (int sv = 0; sv < 6; ++sv)
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    c->max_dsm = optin;
+    for (int sv = 0; sv < 7; ++sv)
         for (int g = 0; g < 2; ++g) {
-            const void *k = solver_kernel(sv, g);
-            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const void *k = sv < 6 ? solver_kernel(sv, g) : (g ? (const void *)k_apply<true> : (const void *)k_apply<false>);
+            cudaFuncAttributes fa;
+            CUDA_TRY(cudaFuncGetAttributes(&fa, k));
+            const int dyn = (optin - (int)fa.sharedSizeBytes) & ~1023;
+            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            c->max_dsm = std::min(c->max_dsm, dyn);
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
@@ -657,7 +866,7 @@ static bool use_grid(int N)
 // ===========================================================================
 template <bool GRID>
 __global__ void __launch_bounds__(kBlock, 1)
-k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl *ctl, double *partials)
+k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl *ctl, double *partials, int cw_off)
 {
     __shared__ TeamShared sh;
     __shared__ DevLdl s_M;
@@ -665,6 +874,8 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
         const int *src = reinterpret_cast<const int *>(&sys->M);
         int *dst = reinterpret_cast<int *>(&s_M);
         for (int i = threadIdx.x; i < (int)(sizeof(DevLdl) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) s_M.cw.smem_off = GRID ? -1 : cw_off;
         __syncthreads();
     }
     PhaseClock pc; pc.start(false, nullptr);
@@ -679,11 +890,13 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
         T.sync();
         return;
     }
-    if (!GRID && M.track_rnorm == 2) {
+    if (!GRID && M.track_rnorm == 2 && M.cw.smem_off >= 0) {
+        // debug timing of the compact walk: cycles of thread 0 in gather / ring wait / steps / scatter
         CtaTeam T; T.init(ctl, nullptr, &sh);
-        PhaseClock dbg; dbg.start(T.leader(), st->phase_cycles);
-        ldl_solve_levels(T, M, in, y, false, &dbg);
+        compact_init(T, M);
+        ldl_solve_compact(T, M, in, y, false, st->phase_cycles);
         T.sync();
+        compact_drain(T, M);
         return;
     }
     if (!GRID && M.track_rnorm == 2) {
@@ -700,8 +913,10 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
         if (T.leader()) { *M.epoch = epoch; if (T.aborted()) st->err = CPK_ERR_TIMEOUT_; }
     } else {
         CtaTeam T; T.init(ctl, nullptr, &sh);
+        compact_init(T, M);
         ldl2_apply(T, M, in, y, epoch, st, pc);
         T.sync();
+        compact_drain(T, M);
         if (T.leader()) { *M.epoch = epoch; if (T.aborted()) st->err = CPK_ERR_TIMEOUT_; }
     }
 }
@@ -777,6 +992,89 @@ int cpk_last_error(char *buf, int64_t buflen)
 
 int64_t cpk_launch_count(void) { return g_launches; }
 
+// Host view of the factors handed to cpk_ldl2_create: permutation vector, D as
+// (d, e, partner), the strict lower triangle of L by rows and by columns, and the
+// dependency level of every row in the two sweeps.
+struct HostLdl {
+    std::vector<int64_t> p;
+    std::vector<double> d, e;
+    std::vector<int> partner;
+    int64_t n2 = 0;
+    HCsr Lrows, Lcols;
+    std::vector<int> lf, lb;
+    int nlf = 0, nlb = 0;
+};
+
+static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int N, HostLdl *H)
+{
+    // ---- permutation
+    H->p.assign(perm, perm + N);
+    std::vector<int64_t> &p = H->p;
+    {
+        std::vector<char> seen(N, 0);
+        for (int k = 0; k < N; ++k) {
+            if (p[k] < 0 || p[k] >= N || seen[p[k]]) return fail(CPK_ERR_ARG, "perm is not a permutation of 0..N-1");
+            seen[p[k]] = 1;
+        }
+    }
+    // ---- D: 1x1 / 2x2 blocks
+    H->d.assign(N, 0.0); H->e.assign(N, 0.0);
+    std::vector<double> &d = H->d, &e = H->e;
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t k = D->colptr[j]; k < D->colptr[j + 1]; ++k) {
+            const int64_t i = D->rowind[k];
+            if (i == j) d[j] = D->val[k];
+            else if (i == j + 1) e[j] = D->val[k];
+            else if (i == j - 1) { /* symmetric twin */ }
+            else if (D->val[k] != 0.0) return fail(CPK_ERR_ARG, "D is not block diagonal with 1x1/2x2 blocks");
+        }
+    H->partner.assign(N, -1);
+    std::vector<int> &partner = H->partner;
+    int64_t &n2 = H->n2;
+    n2 = 0;
+    for (int i = 0; i + 1 < N; ++i)
+        if (e[i] != 0.0) {
+            if (partner[i] >= 0) return fail(CPK_ERR_ARG, "overlapping 2x2 pivots in D");
+            partner[i] = i + 1; partner[i + 1] = i; ++n2;
+        }
+    // ---- L: strict lower triangle, rows (forward deps) and columns (backward deps)
+    HCsr &Lrows = H->Lrows, &Lcols = H->Lcols;
+    {
+        // strip diagonal / reject upper entries
+        std::vector<int64_t> cp(N + 1, 0), ri; std::vector<double> vv;
+        const int64_t nnzL = L->colptr[N];
+        ri.reserve(nnzL); vv.reserve(nnzL);
+        for (int64_t j = 0; j < N; ++j) {
+            for (int64_t k = L->colptr[j]; k < L->colptr[j + 1]; ++k) {
+                const int64_t i = L->rowind[k];
+                if (i < j) { if (L->val[k] != 0.0) return fail(CPK_ERR_ARG, "L is not lower triangular"); continue; }
+                if (i == j) continue;       // unit diagonal
+                ri.push_back(i); vv.push_back(L->val[k]);
+            }
+            cp[j + 1] = (int64_t)ri.size();
+        }
+        cpk_csc Ls{N, N, cp.data(), ri.data(), vv.data()};
+        Lrows = csr_from_csc(Ls);
+        Lcols = csr_of_transpose(Ls);
+    }
+    // ---- dependency levels
+    H->lf.assign(N, 0); H->lb.assign(N, 0);
+    std::vector<int> &lf = H->lf, &lb = H->lb;
+    int &nlf = H->nlf, &nlb = H->nlb;
+    nlf = 0; nlb = 0;
+    for (int i = 0; i < N; ++i) {
+        int lv = 0;
+        for (int64_t k = Lrows.ptr[i]; k < Lrows.ptr[i + 1]; ++k) lv = std::max(lv, lf[Lrows.col[k]] + 1);
+        lf[i] = lv; nlf = std::max(nlf, lv + 1);
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        int lv = 0;
+        for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) lv = std::max(lv, lb[Lcols.col[k]] + 1);
+        lb[i] = lv; nlb = std::max(nlb, lv + 1);
+    }
+    return CPK_OK;
+}
+
 // ---------------------------------------------------------------------------
 int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
                     const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
@@ -797,65 +1095,16 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     int rc = get_device_ctx(device, &dc);
     if (rc) return rc;
 
-    // ---- permutation
-    std::vector<int64_t> p(perm, perm + N);
-    {
-        std::vector<char> seen(N, 0);
-        for (int k = 0; k < N; ++k) {
-            if (p[k] < 0 || p[k] >= N || seen[p[k]]) return fail(CPK_ERR_ARG, "perm is not a permutation of 0..N-1");
-            seen[p[k]] = 1;
-        }
-    }
-    // ---- D: 1x1 / 2x2 blocks
-    std::vector<double> d(N, 0.0), e(N, 0.0);
-    for (int64_t j = 0; j < N; ++j)
-        for (int64_t k = D->colptr[j]; k < D->colptr[j + 1]; ++k) {
-            const int64_t i = D->rowind[k];
-            if (i == j) d[j] = D->val[k];
-            else if (i == j + 1) e[j] = D->val[k];
-            else if (i == j - 1) { /* symmetric twin */ }
-            else if (D->val[k] != 0.0) return fail(CPK_ERR_ARG, "D is not block diagonal with 1x1/2x2 blocks");
-        }
-    std::vector<int> partner(N, -1);
-    int64_t n2 = 0;
-    for (int i = 0; i + 1 < N; ++i)
-        if (e[i] != 0.0) {
-            if (partner[i] >= 0) return fail(CPK_ERR_ARG, "overlapping 2x2 pivots in D");
-            partner[i] = i + 1; partner[i + 1] = i; ++n2;
-        }
-    // ---- L: strict lower triangle, rows (forward deps) and columns (backward deps)
-    HCsr Lrows, Lcols;
-    {
-        // strip diagonal / reject upper entries
-        std::vector<int64_t> cp(N + 1, 0), ri; std::vector<double> vv;
-        const int64_t nnzL = L->colptr[N];
-        ri.reserve(nnzL); vv.reserve(nnzL);
-        for (int64_t j = 0; j < N; ++j) {
-            for (int64_t k = L->colptr[j]; k < L->colptr[j + 1]; ++k) {
-                const int64_t i = L->rowind[k];
-                if (i < j) { if (L->val[k] != 0.0) return fail(CPK_ERR_ARG, "L is not lower triangular"); continue; }
-                if (i == j) continue;       // unit diagonal
-                ri.push_back(i); vv.push_back(L->val[k]);
-            }
-            cp[j + 1] = (int64_t)ri.size();
-        }
-        cpk_csc Ls{N, N, cp.data(), ri.data(), vv.data()};
-        Lrows = csr_from_csc(Ls);
-        Lcols = csr_of_transpose(Ls);
-    }
-    // ---- dependency levels
-    std::vector<int> lf(N, 0), lb(N, 0);
-    int nlf = 0, nlb = 0;
-    for (int i = 0; i < N; ++i) {
-        int lv = 0;
-        for (int64_t k = Lrows.ptr[i]; k < Lrows.ptr[i + 1]; ++k) lv = std::max(lv, lf[Lrows.col[k]] + 1);
-        lf[i] = lv; nlf = std::max(nlf, lv + 1);
-    }
-    for (int i = N - 1; i >= 0; --i) {
-        int lv = 0;
-        for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) lv = std::max(lv, lb[Lcols.col[k]] + 1);
-        lb[i] = lv; nlb = std::max(nlb, lv + 1);
-    }
+    HostLdl HL;
+    rc = parse_ldl(L, D, perm, N, &HL);
+    if (rc) return rc;
+    std::vector<int64_t> &p = HL.p;
+    std::vector<double> &d = HL.d, &e = HL.e;
+    std::vector<int> &partner = HL.partner;
+    const int64_t n2 = HL.n2;
+    HCsr &Lrows = HL.Lrows, &Lcols = HL.Lcols;
+    std::vector<int> &lf = HL.lf, &lb = HL.lb;
+    const int nlf = HL.nlf, nlb = HL.nlb;
     // ---- classify rows and build the unified item list
     std::vector<char> hasR(N), hasC(N), triv(N), fused(N);
     for (int i = 0; i < N; ++i) {
@@ -1044,6 +1293,27 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // (measured on the k=6 windowed stress system, 278+261 levels: 29 ms vs 54 ms per solve)
     m.sync_free = (use_grid(N) && W.lev_f_eff + W.lev_b_eff > 24) ? 1 : 0;
     if (getenv("CPK_LDL_SYNCFREE")) m.sync_free = atoi(getenv("CPK_LDL_SYNCFREE"));
+    // one-CTA team: compact walk (sweep values in shared memory, factor streamed through a
+    // shared-memory ring) whenever its region can fit next to a solver's scratch
+    m.cw.nblk = 0; m.cw.smem_off = -1; m.cw.stream = nullptr; m.cw.perm = nullptr;
+    CwStream cws;
+    {
+        const char *ce = getenv("CPK_LDL_COMPACT");
+        // (below ~24 levels the level walk's two barriers-with-L2-round-trips per level cost less
+        // than the compact walk's gather / scatter of the whole vector; CPK_LDL_COMPACT=1 forces it)
+        const bool deep = nlf + nlb > 24 || (ce && atoi(ce) == 1);
+        if (!use_grid(N) && !(ce && atoi(ce) == 0) && deep && cw_smem_bytes(N) <= (size_t)dc->max_dsm) {
+            cw_sweep(cws, N, Lrows, lf, nlf, 0, 0);         // w_i -= L(i,:) w        target w_i,  deps w
+            cw_dpass(cws, N, d, e, partner);                // y = D^-1 w
+            cw_sweep(cws, N, Lcols, lb, nlb, N, N);         // y_i -= L(:,i)' y       target y_i,  deps y
+            cws.flush();
+            std::vector<int> p32(N);
+            for (int i = 0; i < N; ++i) p32[i] = (int)p[i];
+            CUDA_TRY(o->ar.upload(&m.cw.stream, cws.bytes));
+            CUDA_TRY(o->ar.upload(&m.cw.perm, p32));
+            m.cw.nblk = cws.nblk;
+        }
+    }
     CUDA_TRY(upload_sell(o->ar, sKP, m.KP));
     CUDA_TRY(upload_sell(o->ar, sK12, m.K12));
     CUDA_TRY(upload_sell(o->ar, sK22, m.K22));
@@ -1061,7 +1331,30 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         fprintf(stderr, "[cpk] LDL sweep: N=%d trivial=%lld fused=%lld items=%d (fwd %d) segments=%d levels L %d/%d -> effective %d/%d, tail rows inverted %lld/%lld, warp-rows %lld (longest row %lld), padded entries %zu\n",
                 N, (long long)W.n_trivial, (long long)W.n_fused, W.nitems, W.nfwd, (int)W.seg.size() / 3, nlf, nlb, W.lev_f_eff, W.lev_b_eff,
                 (long long)W.tail_f, (long long)W.tail_b, (long long)W.n_warprow, (long long)W.max_len, W.col.size());
+    if (getenv("CPK_VERBOSE") && m.cw.nblk)
+        fprintf(stderr, "[cpk] compact walk: %d blocks of %d B, %lld levels in %lld steps, %lld items, shared memory %zu B\n",
+                m.cw.nblk, kCwBlock, cws.n_levels, cws.n_steps, cws.n_items, cw_smem_bytes(N));
     *out = register_obj(std::move(o));
+    return CPK_OK;
+}
+
+// debug / test hook (no device needed): the compact-walk stream of a factorization,
+// so that the host-side builder can be checked on a machine without a GPU
+extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, unsigned char *buf, int64_t cap,
+                                   int64_t *nbytes)
+{
+    if (!csc_ok(L) || !csc_ok(D) || !perm || !nbytes) return fail(CPK_ERR_ARG, "cpk_debug_cw_stream: bad argument");
+    const int N = (int)L->nrows;
+    HostLdl HL;
+    int rc = parse_ldl(L, D, perm, N, &HL);
+    if (rc) return rc;
+    CwStream cws;
+    cw_sweep(cws, N, HL.Lrows, HL.lf, HL.nlf, 0, 0);
+    cw_dpass(cws, N, HL.d, HL.e, HL.partner);
+    cw_sweep(cws, N, HL.Lcols, HL.lb, HL.nlb, N, N);
+    cws.flush();
+    *nbytes = (int64_t)cws.bytes.size();
+    if (buf && cap >= *nbytes) memcpy(buf, cws.bytes.data(), cws.bytes.size());
     return CPK_OK;
 }
 
@@ -1145,6 +1438,18 @@ static int status_to_rc(const DevStatus &d, int solver)
 }
 
 // launches a kernel for one team (grid: cooperative; cta: ordinary) and times it
+// dynamic shared memory of a one-CTA launch: [solver scratch `dsm`][compact-walk region].
+// Returns the region's offset (or -1 when the walk is off / does not fit) and grows *total.
+static int cw_place(const DeviceCtx *dc, const DevLdl &m, bool grid, size_t dsm, size_t *total)
+{
+    if (grid || m.cw.nblk == 0) return -1;
+    const size_t off = (dsm + 127) & ~(size_t)127;
+    const size_t need = off + cw_smem_bytes(m.N);
+    if (need > (size_t)dc->max_dsm) return -1;
+    *total = std::max(*total, need);
+    return (int)off;
+}
+
 template <class KG, class KC>
 static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **params, size_t dsm, float *ms)
 {
@@ -1181,9 +1486,11 @@ int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_st
     DevStatus *d_st = M->d_status;
     CUDA_TRY(cudaMemsetAsync(d_st, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = M->d_sys_alone;
-    void *params[] = {(void *)&ps, (void *)&dz, (void *)&dy, (void *)&d_st, (void *)&dc->ctl, (void *)&dc->partials};
+    size_t dsm = 0;
+    int cw_off = cw_place(dc, M->d, use_grid(N), 0, &dsm);
+    void *params[] = {(void *)&ps, (void *)&dz, (void *)&dy, (void *)&d_st, (void *)&dc->ctl, (void *)&dc->partials, (void *)&cw_off};
     float ms = 0.f;
-    rc = launch_team(dc, use_grid(N), k_apply<true>, k_apply<false>, params, 0, &ms);
+    rc = launch_team(dc, use_grid(N), k_apply<true>, k_apply<false>, params, dsm, &ms);
     if (rc) return rc;
     if (mem == CPK_MEM_HOST) CUDA_TRY(cudaMemcpy(y, M->d_y, sizeof(double) * N, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(dc->h_status, d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost));
@@ -1402,13 +1709,15 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
     a.work = S->d_work; a.work_len = (long long)plan.nvec * N;
     a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+    size_t dsm_total = plan.dsm;
+    a.cw_off = cw_place(dc, S->h.M, grid, plan.dsm, &dsm_total);
     CUDA_TRY(cudaMemcpyAsync(S->d_args, &a, sizeof a, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = S->d_sys; const SolveArgs *pa = S->d_args;
     double *wide = dc->wide; int wide_cols = dc->wide_cols;
     void *params[] = {(void *)&ps, (void *)&pa, (void *)&dc->ctl, (void *)&dc->partials, (void *)&wide, (void *)&wide_cols};
     float ms = 0.f;
-    rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, plan.dsm, &ms);
+    rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, dsm_total, &ms);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(dc->h_status, S->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost));
     const DevStatus &st = dc->h_status[0];
@@ -1471,6 +1780,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
     const int64_t cap = cpk_hist_capacity(solver, opts);
     std::vector<DevSystem> hsys(count);
     std::vector<SolveArgs> hargs(count);
+    size_t dsm_total = plan.dsm;
     for (int64_t i = 0; i < count; ++i) {
         System *S = sys[i];
         rc = ensure_buffers(S, plan, cap);
@@ -1485,7 +1795,8 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
         a.work = S->d_work; a.work_len = (long long)plan.nvec * S->h.N;
         a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
-            hargs[i] = a;
+        a.cw_off = cw_place(dc, S->h.M, false, plan.dsm, &dsm_total);
+        hargs[i] = a;
         CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     }
     DevSystem *d_sys = nullptr; SolveArgs *d_args = nullptr;
@@ -1498,7 +1809,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
     {
         double *nullp = nullptr; int zero = 0;
         void *params[] = {(void *)&d_sys, (void *)&d_args, (void *)&dc->ctl, (void *)&nullp, (void *)&nullp, (void *)&zero};
-        CUDA_TRY(cudaLaunchKernel(solver_kernel(solver, false), dim3((unsigned)count), dim3(kBlock), params, plan.dsm, dc->stream));
+        CUDA_TRY(cudaLaunchKernel(solver_kernel(solver, false), dim3((unsigned)count), dim3(kBlock), params, dsm_total, dc->stream));
     }
     ++g_launches;
     CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));

@@ -441,13 +441,254 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
     }
 }
 
+// ---------------------------------------------------------------------------
+// Compact walk (one-CTA team): see DevCompact.  Shared-memory region:
+//   [ring: kCwStages x kCwBlock][mbarrier x kCwStages][ring entries consumed so far][sv: 2N doubles]
+// The ring never stops: entry k holds stream block k mod nblk, and as soon as the
+// CTA is done with an entry the block kCwStages further on is requested, also
+// across the end of a solve -- the next solve finds its first blocks in place.
+// ---------------------------------------------------------------------------
+struct CwSmem {
+    unsigned char *ring;
+    unsigned long long *full;
+    unsigned *count;
+    double *sv;
+    __device__ __forceinline__ explicit CwSmem(int off) {
+        ring = reinterpret_cast<unsigned char *>(g_dsm) + off;
+        full = reinterpret_cast<unsigned long long *>(ring + (size_t)kCwStages * kCwBlock);
+        count = reinterpret_cast<unsigned *>(full + kCwStages);
+        sv = reinterpret_cast<double *>(ring + (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16);
+    }
+    // thread 0: request the stream block of ring entry k
+    __device__ __forceinline__ void issue(const DevCompact &C, unsigned k) const {
+        unsigned long long *bar = &full[k % kCwStages];
+        mbar_expect_tx(bar, kCwBlock);
+        bulk_g2s(ring + (size_t)(k % kCwStages) * kCwBlock, C.stream + (size_t)(k % (unsigned)C.nblk) * kCwBlock, kCwBlock, bar);
+    }
+    template <class Team>
+    __device__ __forceinline__ bool wait(const Team &T, unsigned k) const {
+        unsigned long long *bar = &full[k % kCwStages];
+        const unsigned parity = (k / kCwStages) & 1u;
+        if (mbar_try_wait(bar, parity)) return true;
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar, parity))
+            if (clock64() - t0 > kWatchdogCycles) { T.set_abort(); return false; }
+        return true;
+    }
+};
+
+// once per kernel, before the first solve: barriers + the first ring entries
+template <class Team>
+__device__ __forceinline__ void compact_init(Team &T, const DevLdl &M)
+{
+    if (Team::kKind != 1 || M.cw.smem_off < 0) return;
+    CwSmem W(M.cw.smem_off);
+    if (T.tid == 0) {
+        for (int s = 0; s < kCwStages; ++s) mbar_init(&W.full[s], 1);
+        *W.count = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (unsigned k = 0; k < (unsigned)kCwStages; ++k) W.issue(M.cw, k);
+    }
+    __syncthreads();
+}
+// once per kernel, after the last solve: no bulk copy may be in flight when the CTA exits
+template <class Team>
+__device__ __forceinline__ void compact_drain(Team &T, const DevLdl &M)
+{
+    if (Team::kKind != 1 || M.cw.smem_off < 0) return;
+    CwSmem W(M.cw.smem_off);
+    __syncthreads();
+    if (T.tid == 0) {
+        const unsigned k0 = *W.count;
+        for (unsigned k = k0; k < k0 + (unsigned)kCwStages; ++k) W.wait(T, k);
+    }
+    __syncthreads();
+}
+
+// What a warp does in one step, held in registers.  It is fetched right after the
+// previous step's arithmetic, before the barrier, so that only gather -> arithmetic ->
+// store sit between two barriers.
+constexpr int kCwPre = 8;
+struct CwTask {
+    int kind, width, stride, z;
+    bool barrier;
+    const unsigned char *data;
+    int t;                  // target index in sv, -1 = idle lane
+    int c[kCwPre];
+    double v[kCwPre];
+};
+
+__device__ __forceinline__ void cw_fetch(CwTask &I, const unsigned char *blk, const int4 tk, int lane)
+{
+    I.kind = tk.y & 15; I.barrier = (tk.y & CW_BARRIER) != 0;
+    I.width = (tk.y >> 8) & 0xffff; I.stride = (tk.y >> 24) & 0xff;
+    I.z = tk.z;
+    I.data = blk + tk.x;
+    I.t = -1;
+    I.c[0] = -1; I.c[1] = -1; I.v[0] = 0.0; I.v[1] = 0.0;
+    if (I.kind == CW_ROWS2) {
+        if (lane < I.stride) {
+            const int4 ri = *reinterpret_cast<const int4 *>(I.data + 32 * lane);
+            const double2 rv = *reinterpret_cast<const double2 *>(I.data + 32 * lane + 16);
+            I.t = ri.x; I.c[0] = ri.y; I.c[1] = ri.z; I.v[0] = rv.x; I.v[1] = rv.y;
+        }
+    } else if (I.kind == CW_ROWS || I.kind == CW_WARPROW) {
+        const int stride = I.stride, width = I.width;
+        const bool on = lane < stride;
+        const unsigned char *it = I.data;
+        if (I.kind == CW_ROWS) { if (on) I.t = reinterpret_cast<const int *>(it)[lane]; it += 4 * stride; }
+        else if (lane == 0) I.t = tk.z;
+        I.data = it;
+        const double *val = reinterpret_cast<const double *>(it);
+        const int *col = reinterpret_cast<const int *>(it + (size_t)8 * stride * width);
+        if (width <= 2) {
+            if (on) {
+                I.c[0] = col[lane]; I.v[0] = val[lane];
+                if (width == 2) { I.c[1] = col[stride + lane]; I.v[1] = val[stride + lane]; }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kCwPre; ++u) {
+                const bool have = on && u < width;
+                I.c[u] = have ? col[u * stride + lane] : -1;
+                I.v[u] = have ? val[u * stride + lane] : 0.0;
+            }
+        }
+    }
+}
+
+// sv[t] += -sum_k val_k * sv[col_k], entries in storage order (warp-row: lane partials, butterfly)
+__device__ __forceinline__ void cw_rows(const CwTask &I, double *sv, int lane)
+{
+    const double base = (I.t >= 0) ? sv[I.t] : 0.0;
+    double sum = 0.0;
+    if (I.width <= 2) {
+        const double x0 = (I.c[0] >= 0) ? sv[I.c[0]] : 0.0;
+        const double x1 = (I.c[1] >= 0) ? sv[I.c[1]] : 0.0;
+        if (I.c[0] >= 0) sum -= I.v[0] * x0;
+        if (I.c[1] >= 0) sum -= I.v[1] * x1;
+    } else {
+        double x[kCwPre];
+#pragma unroll
+        for (int u = 0; u < kCwPre; ++u) x[u] = (I.c[u] >= 0) ? sv[I.c[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kCwPre; ++u) if (I.c[u] >= 0) sum -= I.v[u] * x[u];
+        if (I.width > kCwPre && lane < I.stride) {
+            const double *val = reinterpret_cast<const double *>(I.data);
+            const int *col = reinterpret_cast<const int *>(I.data + (size_t)8 * I.stride * I.width);
+            for (int k = kCwPre; k < I.width; ++k) {
+                const int c = col[k * I.stride + lane];
+                if (c >= 0) sum -= val[k * I.stride + lane] * sv[c];
+            }
+        }
+    }
+    if (I.kind == CW_WARPROW) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    }
+    if (I.t >= 0) sv[I.t] = base + sum;
+}
+
+// D chunk, rows 32*warp + lane of it: y_i = w_i / d_i, or the 2x2 solve with the partner
+// row (opLDL2.m:86, inv(op.D))
+__device__ __forceinline__ void cw_dchunk(const CwTask &I, double *sv, int N, int warp, int lane)
+{
+    const int r = 32 * warp + lane, cnt = I.width;
+    if (r >= cnt) return;
+    const double *dd = reinterpret_cast<const double *>(I.data);
+    const double w = sv[I.z + r];
+    double y;
+    if (!I.stride) y = w / dd[r];
+    else {
+        const double *e = dd + cnt, *dp = e + cnt;
+        const int *partner = reinterpret_cast<const int *>(dp + cnt);
+        if (partner[r] < 0) y = w / dd[r];
+        else {
+            const double wp = sv[partner[r]];
+            const double det = dd[r] * dp[r] - e[r] * e[r];
+            y = (dp[r] * w - e[r] * wp) / det;
+        }
+    }
+    sv[N + I.z + r] = y;
+}
+
+template <class Team>
+__device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
+                                               unsigned long long *dbg = nullptr)
+{
+    long long tq = dbg ? clock64() : 0;
+    unsigned long long cyc[4] = {0, 0, 0, 0};       // gather, wait for the ring, steps, scatter
+    auto lap = [&](int slot) { if (dbg) { const long long t = clock64(); cyc[slot] += (unsigned long long)(t - tq); tq = t; } };
+    const DevCompact &C = M.cw;
+    const int N = M.N;
+    if (T.aborted()) return;
+    CwSmem W(C.smem_off);
+    const unsigned k0 = *W.count;
+    const int nblk = C.nblk;
+    const int warp = T.gwarp, lane = T.lane;
+    // w = P' * in: all index loads of a batch first, then all gathers
+    for (int i0 = T.tid; i0 < N; i0 += 8 * T.nthreads) {
+        int pi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? __ldg(&C.perm[i]) : -1; }
+        double zv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) zv[u] = (pi[u] >= 0) ? in(pi[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; if (i < N) W.sv[i] = zv[u]; }
+    }
+    __syncthreads();
+    lap(0);
+    for (int b = 0; b < nblk; ++b) {
+        const unsigned k = k0 + (unsigned)b;
+        if (!W.wait(T, k)) return;
+        lap(1);
+        const unsigned char *blk = W.ring + (size_t)(k % kCwStages) * kCwBlock;
+        const int nsteps = *reinterpret_cast<const int *>(blk);
+        const int4 *slot = reinterpret_cast<const int4 *>(blk + 16) + warp;
+        CwTask cur;
+        cw_fetch(cur, blk, slot[0], lane);
+        bool synced = false;
+        for (int st = 0; st < nsteps; ++st) {
+            if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, N, warp, lane);
+            else if (cur.kind != 0) cw_rows(cur, W.sv, lane);
+            synced = cur.barrier;
+            if (st + 1 < nsteps) cw_fetch(cur, blk, slot[(st + 1) * kWarpsPerCta], lane);
+            if (synced) __syncthreads();
+        }
+        if (!synced) __syncthreads();           // every warp is done with this ring entry
+        if (T.tid == 0) W.issue(C, k + (unsigned)kCwStages);
+        lap(2);
+    }
+    // out = P * y
+    for (int i0 = T.tid; i0 < N; i0 += 8 * T.nthreads) {
+        int pi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? __ldg(&C.perm[i]) : -1; }
+        if (accumulate) {
+            double ov[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ov[u] = (pi[u] >= 0) ? out[pi[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = ov[u] + W.sv[N + i0 + u * T.nthreads];
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = W.sv[N + i0 + u * T.nthreads];
+        }
+    }
+    if (T.tid == 0) *W.count = k0 + (unsigned)nblk;
+    lap(3);
+    if (dbg && T.tid == 0) for (int q = 0; q < 4; ++q) dbg[q] = cyc[q];
+}
+
 // y = P * L^-T * D^-1 * L^-1 * P' * in   (opLDL2.m:86, right to left).
 // If `accumulate`, out[p] += y (the y = y + dy of opLDL2.m:181).  Ends WITHOUT a
 // team barrier: the caller syncs before `out` is gathered.
 template <class Team>
 __device__ __forceinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate, int epoch)
 {
-    if (M.sync_free) ldl_solve_syncfree(T, M, in, out, accumulate, epoch);
+    if (Team::kKind == 1 && M.cw.smem_off >= 0) ldl_solve_compact(T, M, in, out, accumulate);
+    else if (M.sync_free) ldl_solve_syncfree(T, M, in, out, accumulate, epoch);
     else ldl_solve_levels(T, M, in, out, accumulate, (PhaseClock *)nullptr);
 }
 

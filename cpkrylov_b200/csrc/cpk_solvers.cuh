@@ -783,6 +783,7 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
     SolveArgs A = A0;
     Ctx<Team> c{T, S, A, A.status, PhaseClock(), 0, dsm, S.n, S.m, S.N};
     c.epoch = *S.M.epoch;       // flags of earlier launches carry earlier epochs
+    compact_init(T, S.M);
     const int n = S.n, N = S.N;
     c.pc.start(A.profile && T.leader(), A.status->phase_cycles);
     // two reserved N-vectors at the end of the workspace: XY0 and B1
@@ -822,6 +823,7 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
         TEAM_FOR(T, i, N) X[i] = XY0[i] + X[i];
     }
     T.sync();
+    compact_drain(T, S.M);
     c.pc.mark(CPK_PH_OTHER_);
     if (T.leader()) {
         *S.M.epoch = c.epoch;
@@ -831,8 +833,6 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
 
 // One persistent kernel per (solver, team kind).  GRID: cooperative launch, the
 // whole grid works on sys[0]; otherwise CTA b works on sys[b] (batch).
-extern __shared__ double g_dsm[];
-
 template <int SOLVER, bool GRID>
 __global__ void __launch_bounds__(kBlock, 1)
 k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols)
@@ -850,6 +850,8 @@ k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *parti
         src = reinterpret_cast<const int *>(args + idx);
         dst = reinterpret_cast<int *>(&s_args);
         for (int i = threadIdx.x; i < (int)(sizeof(SolveArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) s_sys.M.cw.smem_off = GRID ? -1 : s_args.cw_off;     // per launch: depends on the solver's scratch
         __syncthreads();
     }
     if (GRID) {
