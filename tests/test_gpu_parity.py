@@ -89,11 +89,16 @@ def test_exprog2_nonsymmetric(cp, meth, extra, kind, team):
 
 @pytest.mark.parametrize("team", ["cta", "grid"])
 @pytest.mark.parametrize("env", [{"CPK_LDL_SYNCFREE": "1"}, {"CPK_LDL_NO_SHORTCUTS": "1"}, {"CPK_LDL_NO_TAIL": "1"},
-                                 {"CPK_LDL_SYNCFREE": "1", "CPK_LDL_NO_TAIL": "1"}])
+                                 {"CPK_LDL_SYNCFREE": "1", "CPK_LDL_NO_TAIL": "1"}, {}, {"CPK_LDL_COMPACT": "1"}])
 def test_ldl_walk_variants_agree(cp, env, team):
-    """The LDL' solve has two walks (level-synchronous, sync-free/tagged) and setup
-    shortcuts (trivial/fused rows, tail inversion); every combination must give the
-    oracle's answer (the switches are read when the operator is created)."""
+    """The LDL' solve has three walks (level-synchronous, sync-free/tagged, and the
+    shared-memory compact walk of the one-CTA team) and setup shortcuts (trivial/fused
+    rows, tail inversion); every combination must give the oracle's answer (the
+    switches are read when the operator is created).  The global-memory walks of the
+    one-CTA team are reached with CPK_LDL_COMPACT=0; CPK_LDL_COMPACT=1 forces the
+    compact walk on the shallow cvxqp2 factor as well."""
+    if team == "cta" and "CPK_LDL_COMPACT" not in env and env:
+        env = dict(env, CPK_LDL_COMPACT="0")
     s = load_system("cvxqp1_m")
     fac = load_factors("cvxqp1_m", "superlu")
     os.environ.update(env)
@@ -106,12 +111,15 @@ def test_ldl_walk_variants_agree(cp, env, team):
             os.environ.pop(k, None)
 
 
-def test_exprog1_dense_bk_2x2_pivots(cp):
+@pytest.mark.parametrize("team", ["grid", "cta"])
+def test_exprog1_dense_bk_2x2_pivots(cp, team):
+    """Dense Bunch-Kaufman factor of cvxqp1: many 2x2 pivots, rows of thousands of entries
+    (one-CTA team: the compact walk splits them into ordered parts of 512)."""
     from cpkrylov_b200.ldl import ldl_dense_bk
     s = load_system("cvxqp1_m")
     fac = ldl_dense_bk(kp_of(s))
     assert np.count_nonzero(fac[2]) > 100                   # many 2x2 pivots (SURVEY section 4)
-    _compare(cp, s, fac, "cpminres", dict(EX_OPTS), "grid")
+    _compare(cp, s, fac, "cpminres", dict(EX_OPTS), team)
 
 
 @pytest.mark.parametrize("team", ["cta", "grid"])
