@@ -711,6 +711,9 @@ struct DeviceCtx {
     DevStatus *h_status = nullptr;  // pinned
     int h_status_cap = 0;
     int max_dsm = 0;                // dynamic shared memory every solver / apply kernel may ask for
+    // batch launches: pinned staging for right-hand sides / solutions, descriptor arrays
+    double *h_stage = nullptr, *d_stage = nullptr; size_t h_stage_cap = 0;      // doubles
+    DevSystem *d_bsys = nullptr; SolveArgs *d_bargs = nullptr; DevStatus *d_bstatus = nullptr; size_t d_batch_cap = 0;
 };
 constexpr int kMaxBatch = 4096;
 static std::mutex g_mu;
@@ -1781,6 +1784,35 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
     std::vector<DevSystem> hsys(count);
     std::vector<SolveArgs> hargs(count);
     size_t dsm_total = plan.dsm;
+    // one pinned staging area for all right-hand sides and solutions: the copies of the whole
+    // batch are queued asynchronously around the single launch
+    std::vector<size_t> off(count + 1, 0);
+    for (int64_t i = 0; i < count; ++i) off[i + 1] = off[i] + (size_t)sys[i]->h.N;
+    const size_t tot = off[count];
+    const bool want_hist = hist && hist_cap > 0;
+    const size_t hrows = solver == CPK_CPSYMMLQ ? 3 : 1;
+    const size_t htot = want_hist ? (size_t)count * 3 * (size_t)cap : 0;    // device layout: 3 rows of `cap` per system
+    const size_t need = 2 * tot + htot;
+    if (need > dc->h_stage_cap) {
+        if (dc->h_stage) cudaFreeHost(dc->h_stage);
+        if (dc->d_stage) cudaFree(dc->d_stage);
+        dc->h_stage = nullptr; dc->d_stage = nullptr; dc->h_stage_cap = 0;
+        CUDA_TRY(cudaMallocHost(&dc->h_stage, sizeof(double) * need));
+        CUDA_TRY(cudaMalloc(&dc->d_stage, sizeof(double) * need));
+        dc->h_stage_cap = need;
+    }
+    if ((size_t)count > dc->d_batch_cap) {
+        if (dc->d_bsys) cudaFree(dc->d_bsys);
+        if (dc->d_bargs) cudaFree(dc->d_bargs);
+        if (dc->d_bstatus) cudaFree(dc->d_bstatus);
+        dc->d_bsys = nullptr; dc->d_bargs = nullptr; dc->d_bstatus = nullptr; dc->d_batch_cap = 0;
+        CUDA_TRY(cudaMalloc(&dc->d_bsys, sizeof(DevSystem) * count));
+        CUDA_TRY(cudaMalloc(&dc->d_bargs, sizeof(SolveArgs) * count));
+        CUDA_TRY(cudaMalloc(&dc->d_bstatus, sizeof(DevStatus) * count));
+        dc->d_batch_cap = (size_t)count;
+    }
+    double *hb = dc->h_stage, *hx = dc->h_stage + tot;
+    double *db = dc->d_stage, *dx = dc->d_stage + tot;
     for (int64_t i = 0; i < count; ++i) {
         System *S = sys[i];
         rc = ensure_buffers(S, plan, cap);
@@ -1789,19 +1821,20 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         hsys[i] = S->h;
         SolveArgs a{};
         a.solver = solver; a.reg_mode = 1;
-        CUDA_TRY(cudaMemcpyAsync(S->d_b, b[i], sizeof(double) * S->h.N, cudaMemcpyHostToDevice, dc->stream));
-        a.b = S->d_b; a.x = S->d_x;
+        if (!b[i] || !x[i]) return fail(CPK_ERR_ARG, "batch entry %lld: null vector", (long long)i);
+        memcpy(hb + off[i], b[i], sizeof(double) * S->h.N);
+        a.b = db + off[i]; a.x = dx + off[i];
         a.atol = opts->atol; a.rtol = opts->rtol; a.btol = opts->btol; a.itmax = opts->itmax;
         a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
         a.work = S->d_work; a.work_len = (long long)plan.nvec * S->h.N;
-        a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
+        a.hist = want_hist ? dc->d_stage + 2 * tot + (size_t)i * 3 * cap : S->d_hist;
+        a.hist_cap = cap; a.gs = S->d_gs; a.status = dc->d_bstatus + i;
         a.cw_off = cw_place(dc, S->h.M, false, plan.dsm, &dsm_total);
         hargs[i] = a;
-        CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     }
-    DevSystem *d_sys = nullptr; SolveArgs *d_args = nullptr;
-    CUDA_TRY(cudaMalloc(&d_sys, sizeof(DevSystem) * count));
-    CUDA_TRY(cudaMalloc(&d_args, sizeof(SolveArgs) * count));
+    CUDA_TRY(cudaMemcpyAsync(db, hb, sizeof(double) * tot, cudaMemcpyHostToDevice, dc->stream));
+    CUDA_TRY(cudaMemsetAsync(dc->d_bstatus, 0, sizeof(DevStatus) * count, dc->stream));
+    DevSystem *d_sys = dc->d_bsys; SolveArgs *d_args = dc->d_bargs;
     CUDA_TRY(cudaMemcpyAsync(d_sys, hsys.data(), sizeof(DevSystem) * count, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemcpyAsync(d_args, hargs.data(), sizeof(SolveArgs) * count, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemsetAsync(dc->ctl, 0, sizeof(TeamCtl) * count, dc->stream));
@@ -1813,23 +1846,22 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
     }
     ++g_launches;
     CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    CUDA_TRY(cudaMemcpyAsync(dc->h_status, dc->d_bstatus, sizeof(DevStatus) * count, cudaMemcpyDeviceToHost, dc->stream));
+    CUDA_TRY(cudaMemcpyAsync(hx, dx, sizeof(double) * (tot + htot), cudaMemcpyDeviceToHost, dc->stream));     // solutions (+ histories)
     CUDA_TRY(cudaStreamSynchronize(dc->stream));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, dc->ev0, dc->ev1));
-    cudaFree(d_sys); cudaFree(d_args);
     int first_rc = CPK_OK;
     std::string first_msg;
     for (int64_t i = 0; i < count; ++i) {
         System *S = sys[i];
-        CUDA_TRY(cudaMemcpy(&dc->h_status[i], S->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(x[i], S->d_x, sizeof(double) * S->h.N, cudaMemcpyDeviceToHost));
+        memcpy(x[i], hx + off[i], sizeof(double) * S->h.N);
         const DevStatus &st = dc->h_status[i];
-        if (hist && hist[i] && hist_cap > 0) {
-            const int rows = solver == CPK_CPSYMMLQ ? 3 : 1;
+        if (want_hist && hist[i]) {
             const int64_t len = std::min<int64_t>(std::min<int64_t>(st.hist_len, cap), hist_cap);
-            for (int r = 0; r < rows; ++r)
-                if (len > 0)
-                    CUDA_TRY(cudaMemcpy(hist[i] + (size_t)r * hist_cap, S->d_hist + (size_t)r * cap, sizeof(double) * len, cudaMemcpyDeviceToHost));
+            const double *hh = dc->h_stage + 2 * tot + (size_t)i * 3 * cap;
+            for (size_t r = 0; r < hrows; ++r)
+                if (len > 0) memcpy(hist[i] + r * hist_cap, hh + r * cap, sizeof(double) * len);
         }
         if (stats) fill_stats(&stats[i], st, ms, i == 0 ? 1 : 0);
         const int r = status_to_rc(st, solver);
