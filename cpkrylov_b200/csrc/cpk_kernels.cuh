@@ -650,10 +650,11 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
         cw_fetch(cur, blk, slot[0], lane);
         bool synced = false;
         for (int st = 0; st < nsteps; ++st) {
+            const int4 tk = slot[min(st + 1, nsteps - 1) * kWarpsPerCta];    // next slot: its latency hides behind the arithmetic
             if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, N, warp, lane);
             else if (cur.kind != 0) cw_rows(cur, W.sv, lane);
             synced = cur.barrier;
-            if (st + 1 < nsteps) cw_fetch(cur, blk, slot[(st + 1) * kWarpsPerCta], lane);
+            if (st + 1 < nsteps) cw_fetch(cur, blk, tk, lane);
             if (synced) __syncthreads();
         }
         if (!synced) __syncthreads();           // every warp is done with this ring entry

@@ -509,6 +509,27 @@ __device__ void multi_dot(Ctx<Team> &c, const double *VQ, const int *cols, int n
 {
     Team &T = c.T;
     const int N = c.N;
+    if (Team::kKind == 1 && N <= 8192) {
+        // one-CTA team, short vectors: a warp per column (all loads of a column independent,
+        // one butterfly, no CTA barrier per chunk of columns)
+        __syncthreads();                    // hs is free (previous coefficients consumed)
+        for (int j = T.gwarp; j < nc; j += T.nwarps) {
+            const double *col = VQ + (size_t)cols[j] * N;
+            double acc = 0.0;
+            for (int i0 = T.lane; i0 < N; i0 += 128) {
+                double a[4], u[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int i = i0 + 32 * q; a[q] = (i < N) ? col[i] : 0.0; u[q] = (i < N) ? U[i] : 0.0; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc += a[q] * u[q];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (T.lane == 0) hs[j] = acc;
+        }
+        __syncthreads();
+        return;
+    }
     for (int j0 = 0; j0 < nc; j0 += kRedMax) {
         const int nv = min(kRedMax, nc - j0);
         double acc[kRedMax];
