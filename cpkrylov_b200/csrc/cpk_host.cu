@@ -805,9 +805,13 @@ static int get_device_ctx(int device, DeviceCtx **out)
             const void *k = sv < 6 ? solver_kernel(sv, g) : (g ? (const void *)k_apply<true> : (const void *)k_apply<false>);
             cudaFuncAttributes fa;
             CUDA_TRY(cudaFuncGetAttributes(&fa, k));
-            const int dyn = (optin - (int)fa.sharedSizeBytes) & ~1023;
+            int dyn = (optin - (int)fa.sharedSizeBytes) & ~1023;
+            if (g) {
+                // grid kernels only ever need the GMRES/DQGMRES scratch
+                static const int grid_kb = [] { const char *e = getenv("CPK_GRID_DSM_KB"); return e ? atoi(e) : 200; }();
+                dyn = std::min(dyn, grid_kb * 1024);
+            } else c->max_dsm = std::min(c->max_dsm, dyn);
             CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-            c->max_dsm = std::min(c->max_dsm, dyn);
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
