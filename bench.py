@@ -208,11 +208,17 @@ def run_batch(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    base = synth.load_cvxqp1()
     lo, hi = partition(args.batch, world, rank)
     opts = dict(atol=1e-6, rtol=1e-6, itmax=500, residual_update=True, nitref=1, force_itref=True)
     t0 = time.perf_counter()
-    systems = [synth.ipm_batch_system(base, j) for j in range(lo, hi)]
+    if args.g > 0:
+        # larger variant: cfg-3 pattern on a g^3 grid; systems beyond the one-CTA
+        # limit share cooperative launches as sub-teams of the grid
+        systems = [synth.ipm_batch_lap3d(args.g, j) for j in range(lo, hi)]
+        base = dict(n=systems[0]["n"], m=systems[0]["m"], N=systems[0]["n"] + systems[0]["m"])
+    else:
+        base = synth.load_cvxqp1()
+        systems = [synth.ipm_batch_system(base, j) for j in range(lo, hi)]
     facs = [ldl_superlu(synth.kp_matrix(w)) for w in systems]
     bs = BatchSolver(systems, facs, opts, device=local_rank)
     t_setup = time.perf_counter() - t0
@@ -225,10 +231,12 @@ def run_batch(args, rank, local_rank, world):
     t1 = time.perf_counter()
     iters = 0
     dev_ms = 0.0
+    launches = 0
     for _ in range(args.steps):
         xs, st = bs.solve("cpminres", rhs, opts)
         iters += sum(d["niters"] for d in st)
         dev_ms += bs.last_ms
+        launches += bs.last_launches
         if world > 1:
             red = torch.tensor([min(int(d["solved"]) for d in st)], device="cuda")
             dist.all_reduce(red, op=dist.ReduceOp.MIN)
@@ -247,12 +255,12 @@ def run_batch(args, rank, local_rank, world):
             "metric": "krylov_iterations_per_second", "value": cnt.item() / wall_max, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ipm_batch", "systems": args.batch, "n": base["n"], "m": base["m"], "solver": "cpminres",
+            "config": {"workload": "ipm_batch", "g": args.g, "systems": args.batch, "n": base["n"], "m": base["m"], "solver": "cpminres",
                        "opts": opts, "systems_per_rank": hi - lo, "device_ms_per_step": dev_max / args.steps,
                        "setup_s": t_setup, "note": "end to end through the host-pointer batch ABI (H2D rhs, D2H solutions inside the timed region)"},
             "e2e": {"value": cnt.item() / wall_max, "unit": "iterations/s",
                     "h2d_bytes_per_step": 8 * base["N"] * (hi - lo), "d2h_bytes_per_step": 8 * base["N"] * (hi - lo)},
-            "gpu_launches": args.steps}))
+            "gpu_launches": launches}))
     bs.close()
     if world > 1:
         dist.destroy_process_group()

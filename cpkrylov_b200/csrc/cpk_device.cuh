@@ -283,10 +283,17 @@ struct GridTeam {
     TeamShared *sh;
     unsigned bar_target;
     unsigned red_parity;
+    // a team is `nblk` consecutive CTAs of the cooperative grid (the whole grid, or one of
+    // several sub-teams that each solve their own system): bid = CTA index inside the team,
+    // base = first CTA of the team in the grid
+    int bid, nblk, base;
 
-    __device__ void init(TeamCtl *c, double *p, TeamShared *s) {
-        tid = blockIdx.x * blockDim.x + threadIdx.x;
-        nthreads = gridDim.x * blockDim.x;
+    __device__ void init(TeamCtl *c, double *p, TeamShared *s, int team_ctas = 0) {
+        nblk = team_ctas > 0 ? team_ctas : (int)gridDim.x;
+        bid = (int)blockIdx.x % nblk;
+        base = (int)blockIdx.x - bid;
+        tid = bid * blockDim.x + threadIdx.x;
+        nthreads = nblk * blockDim.x;
         gwarp = tid >> 5;
         nwarps = nthreads >> 5;
         lane = threadIdx.x & 31;
@@ -303,7 +310,7 @@ struct GridTeam {
     __device__ void sync() {
         __syncthreads();
         if (threadIdx.x == 0) {
-            bar_target += gridDim.x;
+            bar_target += (unsigned)nblk;
             red_release_add(&ctl->bar, 1u);
             unsigned spins = 0;
             long long t0 = clock64();
@@ -339,14 +346,14 @@ struct GridTeam {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                 if (lane == 0)
-                    st_cg(&partials[((size_t)red_parity * kRedMax + k) * gridDim.x + blockIdx.x], s);
+                    st_cg(&partials[((size_t)red_parity * kRedMax + k) * gridDim.x + blockIdx.x], s);      // blockIdx.x = base + bid
             }
         }
         sync();
         if (w < K) {
-            const double *p = &partials[((size_t)red_parity * kRedMax + w) * gridDim.x];
+            const double *p = &partials[((size_t)red_parity * kRedMax + w) * gridDim.x + base];
             double s = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) s += ld_cg(&p[b]);
+            for (int b = lane; b < nblk; b += 32) s += ld_cg(&p[b]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
             if (lane == 0) sh->out[w] = s;
@@ -391,9 +398,9 @@ struct GridTeam {
         sync();
         const int w = threadIdx.x >> 5;
         for (int c = w; c < ncols; c += kWarpsPerCta) {
-            const double *p = &wide[((size_t)wide_parity * wide_cols + c) * gridDim.x];
+            const double *p = &wide[((size_t)wide_parity * wide_cols + c) * gridDim.x + base];
             double s = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) s += ld_cg(&p[b]);
+            for (int b = lane; b < nblk; b += 32) s += ld_cg(&p[b]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
             if (lane == 0) dst[c] = s;

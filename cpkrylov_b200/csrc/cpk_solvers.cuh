@@ -856,7 +856,7 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
 // whole grid works on sys[0]; otherwise CTA b works on sys[b] (batch).
 template <int SOLVER, bool GRID>
 __global__ void __launch_bounds__(kBlock, 1)
-k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols)
+k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols, int team_ctas)
 {
     __shared__ TeamShared sh;
     // the operator descriptors are read all the time: keep a CTA-local copy in
@@ -864,7 +864,8 @@ k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *parti
     __shared__ DevSystem s_sys;
     __shared__ SolveArgs s_args;
     {
-        const int idx = GRID ? 0 : blockIdx.x;
+        // GRID: the grid is one team, or (team_ctas > 0) consecutive sub-teams of team_ctas CTAs, team t on sys[t]
+        const int idx = GRID ? (team_ctas > 0 ? (int)blockIdx.x / team_ctas : 0) : (int)blockIdx.x;
         const int *src = reinterpret_cast<const int *>(sys + idx);
         int *dst = reinterpret_cast<int *>(&s_sys);
         for (int i = threadIdx.x; i < (int)(sizeof(DevSystem) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
@@ -877,7 +878,7 @@ k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *parti
     }
     if (GRID) {
         GridTeam T;
-        T.init(ctl, partials, &sh);
+        T.init(ctl + (team_ctas > 0 ? (int)blockIdx.x / team_ctas : 0), partials, &sh, team_ctas);
         T.wide = wide; T.wide_cols = wide_cols;
         solve_entry<SOLVER>(T, s_sys, s_args, g_dsm);
     } else {

@@ -91,6 +91,19 @@ def ipm_batch_system(base, j, nZ=2000):
                 params=dict(workload="ipm_batch", j=j, nZ=nZ, seed=100 + j))
 
 
+def ipm_batch_lap3d(g, j, k=2):
+    """cfg 5, larger variant (g=40, n=64 000, m=16 000): system j of an
+    IPM-like sequence on the cfg-3 pattern.  H_j = Laplacian + diag(rho), rho = 10^u,
+    u ~ U(-2, 2), seed 100 + j (the positive diagonal S^-1 Z + rho I of an interior-point
+    iteration, examples/cpk_exprog1.m:13-16); B, C and the right-hand side recipe are shared."""
+    base = kkt_lap3d(g=g, k=k)
+    n = base["n"]
+    rng = np.random.default_rng(100 + j)
+    H = (base["H"] + sp.diags(10.0 ** rng.uniform(-2.0, 2.0, size=n))).tocsc()
+    w = _finish(H, base["B"], 1e-6, 3, dict(workload="ipm_batch_lap3d", g=g, k=k, j=j, seed=100 + j))
+    return w
+
+
 def load_cvxqp1():
     """The reference's example system (tests/golden/cvxqp1_m_system.npz)."""
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

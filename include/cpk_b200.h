@@ -180,8 +180,12 @@ int  cpk_reg_solve(cpk_handle S, int solver, const double *b, const cpk_opts *op
 /* history length needed for (solver, opts): itmax+1 (+ a restart cycle for cpgmres) */
 int64_t cpk_hist_capacity(int solver, const cpk_opts *opts);
 
-/* Batch of independent systems on one GPU in ONE launch (one CTA per system):
- * the sharded unit of the multi-GPU path.  All systems must live on the same
+/* Batch of independent systems on one GPU: the sharded unit of the multi-GPU path
+ * (what a loop over reg_cpkrylov.m:1 calls does for the systems of an interior-point
+ * run).  Systems small enough for a one-CTA team share ONE launch (CTA t solves system
+ * t); larger ones share cooperative launches whose grid is cut into sub-teams of
+ * consecutive CTAs, one system per sub-team, as many waves as needed
+ * (stats[0].launches = launches of the whole call).  All systems must live on the same
  * device.  b/x: arrays of `count` host pointers (N_i each); hist may be NULL or
  * `count` pointers to 3*hist_cap doubles. */
 int  cpk_batch_reg_solve(const cpk_handle *S, int64_t count, int solver, const double *const *b,

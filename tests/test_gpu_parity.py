@@ -326,3 +326,31 @@ def test_batch_of_ipm_systems_one_launch(cp):
         if fo["solved"]:
             assert relerr(xg, xo) < 1e-8
     bs.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("meth,extra", [("cpcg", {}), ("cpdqgmres", {"mem": 8})])
+def test_batch_of_mid_size_systems_in_sub_teams(cp, meth, extra):
+    """Systems too large for one CTA: the cooperative grid is cut into sub-teams, one system
+    each, several systems per launch; a small system in the same call still goes to the one-CTA
+    launch.  Every solution must match the CPU restatement and the whole-grid solve."""
+    from cpkrylov_b200 import synth
+    from cpkrylov_b200.ldl import ldl_superlu
+    from cpkrylov_b200.batch import BatchSolver
+    systems = [synth.kkt_lap3d(g=32, k=2, seed_B=10 + j, seed_x=20 + j) for j in range(5)]      # N = 40 960 each
+    small = synth.ipm_batch_system(synth.load_cvxqp1(), 0)
+    systems.insert(2, small)
+    facs = [ldl_superlu(synth.kp_matrix(w)) for w in systems]
+    o = dict(EX_OPTS, **extra)          # the example options keep the ill-conditioned IPM system inside attainable accuracy
+    bs = BatchSolver(systems, facs, o)
+    try:
+        xs, stats = bs.solve(meth, [w["rhs"] for w in systems], o)
+        assert 2 <= bs.last_launches <= 3                   # one CTA launch + one or two sub-team waves
+        for j, (w, f, xg, st) in enumerate(zip(systems, facs, xs, stats)):
+            xo, so, fo = orc.reg_cpkrylov(meth, w["rhs"], w["H"], w["B"], w["C"], w["G"], o, factor=lambda K, f=f: f)
+            assert st["solved"] == fo["solved"] and abs(st["niters"] - so["niters"]) <= 2, j
+            assert relerr(xg, xo) < 1e-7, (j, relerr(xg, xo))
+            x1, s1, f1 = cp.reg_cpkrylov(meth, w["rhs"], w["H"], w["B"], w["C"], w["G"], o, factors=f)
+            assert relerr(xg, x1) < 1e-8 and s1["niters"] == st["niters"], j
+    finally:
+        bs.close()
