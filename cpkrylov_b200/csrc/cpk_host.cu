@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <chrono>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -593,6 +594,11 @@ static void cw_dpass(CwStream &S, int N, const std::vector<double> &d, const std
     S.level(items);
 }
 
+// Device memory of one object.  Arrays come from the device's stream-ordered pool
+// (cudaMallocAsync on the legacy stream, release threshold = keep everything): a small system
+// needs ~50 arrays and plain cudaMalloc was half of its set-up time, while large chunks
+// from cudaMalloc proved erratic (3 .. 200 ms).  Every allocation is followed by a synchronous
+// copy or by the synchronization at the end of the create call before anything uses it.
 struct DevArena {
     std::vector<void *> ptrs;
     int device = 0;
@@ -600,16 +606,17 @@ struct DevArena {
     void release() {
         if (ptrs.empty()) return;
         cudaSetDevice(device);
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) cudaFreeAsync(p, (cudaStream_t)0);
         ptrs.clear();
     }
     template <class T>
     cudaError_t alloc(T **out, size_t count, bool zero = false) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        cudaError_t e = cudaMallocAsync(&p, bytes, (cudaStream_t)0);
         if (e != cudaSuccess) return e;
         ptrs.push_back(p);
-        if (zero) { e = cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)); if (e != cudaSuccess) return e; }
+        if (zero) { e = cudaMemsetAsync(p, 0, bytes, (cudaStream_t)0); if (e != cudaSuccess) return e; }
         *out = (T *)p;
         return cudaSuccess;
     }
@@ -618,7 +625,7 @@ struct DevArena {
         T *p = nullptr;
         cudaError_t e = alloc(&p, v.size());
         if (e != cudaSuccess) return e;
-        if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (!v.empty()) e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)0);
         *out = p;
         return e;
     }
@@ -818,6 +825,12 @@ static int get_device_ctx(int device, DeviceCtx **out)
     c->grid_blocks = c->num_sms;    // one CTA per SM
     if (const char *e = getenv("CPK_GRID_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= c->num_sms * per_sm) c->grid_blocks = v; }
     g_grid_warps_hint = c->grid_blocks * kWarpsPerCta;
+    {
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;        // freed arrays stay in the pool for the next system
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -1102,9 +1115,14 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     int rc = get_device_ctx(device, &dc);
     if (rc) return rc;
 
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     HostLdl HL;
     rc = parse_ldl(L, D, perm, N, &HL);
     if (rc) return rc;
+    const double t_parse = ms_since(t_begin);
     std::vector<int64_t> &p = HL.p;
     std::vector<double> &d = HL.d, &e = HL.e;
     std::vector<int> &partner = HL.partner;
@@ -1127,6 +1145,12 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // triangular tail block, built row by row), so the whole tail becomes ONE
     // level that depends only on earlier levels and on the input vector.
     // Skipped when the substitution would fill in or grow too much.
+    // a system that will walk the compact stream keeps the global sweep only as a fallback
+    // (a solver scratch too large for the stream's shared memory): no tail inversion for it,
+    // which is most of the host-side set-up time of a small system
+    const char *cenv = getenv("CPK_LDL_COMPACT");
+    const bool compact_walk = !use_grid(N) && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)) &&
+                              cw_smem_bytes(N) <= (size_t)dc->max_dsm;
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
@@ -1165,7 +1189,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         }
         int maxlev = 0;
         int cut = choose_cut(levf, triv, maxlev);
-        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL"); ++attempt, cut += (maxlev - cut + 1) / 2) {
+        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL") && !compact_walk; ++attempt, cut += (maxlev - cut + 1) / 2) {
             long long orig = 0, fill = 0;
             double growth = 0.0;
             bool okinv = true;
@@ -1223,7 +1247,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         }
         int maxlev = 0;
         int cut = choose_cut(levb, fused, maxlev);
-        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL"); ++attempt, cut += (maxlev - cut + 1) / 2) {
+        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL") && !compact_walk; ++attempt, cut += (maxlev - cut + 1) / 2) {
             bool tail_has_2x2 = false;
             for (int i = 0; i < N; ++i) if (!fused[i] && levb[i] >= cut && partner[i] >= 0) tail_has_2x2 = true;
             if (tail_has_2x2) continue;
@@ -1277,12 +1301,14 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     }
     for (int i = 0; i < N; ++i) { W.n_trivial += triv[i]; W.n_fused += fused[i]; }
     if ((int64_t)W.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
+    const double t_sweeps = ms_since(t_begin);
     // ---- K_P = [A B'; B C] by rows
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, (int)nA, (int)nC);
     HSell sKP = build_sell(KP), sK12 = build_sell(Bt), sK22 = build_sell(Cr);
     if ((int64_t)sKP.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
 
+    const double t_sell = ms_since(t_begin);
     // ---- upload
     auto o = std::make_unique<Ldl2>();
     o->device = device; o->ar.device = device;
@@ -1305,11 +1331,9 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     m.cw.nblk = 0; m.cw.smem_off = -1; m.cw.stream = nullptr; m.cw.perm = nullptr;
     CwStream cws;
     {
-        const char *ce = getenv("CPK_LDL_COMPACT");
         // (below ~24 levels the level walk's two barriers-with-L2-round-trips per level cost less
         // than the compact walk's gather / scatter of the whole vector; CPK_LDL_COMPACT=1 forces it)
-        const bool deep = nlf + nlb > 24 || (ce && atoi(ce) == 1);
-        if (!use_grid(N) && !(ce && atoi(ce) == 0) && deep && cw_smem_bytes(N) <= (size_t)dc->max_dsm) {
+        if (compact_walk) {
             cw_sweep(cws, N, Lrows, lf, nlf, 0, 0);         // w_i -= L(i,:) w        target w_i,  deps w
             cw_dpass(cws, N, d, e, partner);                // y = D^-1 w
             cw_sweep(cws, N, Lcols, lb, nlb, N, N);         // y_i -= L(:,i)' y       target y_i,  deps y
@@ -1338,9 +1362,27 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         fprintf(stderr, "[cpk] LDL sweep: N=%d trivial=%lld fused=%lld items=%d (fwd %d) segments=%d levels L %d/%d -> effective %d/%d, tail rows inverted %lld/%lld, warp-rows %lld (longest row %lld), padded entries %zu\n",
                 N, (long long)W.n_trivial, (long long)W.n_fused, W.nitems, W.nfwd, (int)W.seg.size() / 3, nlf, nlb, W.lev_f_eff, W.lev_b_eff,
                 (long long)W.tail_f, (long long)W.tail_b, (long long)W.n_warprow, (long long)W.max_len, W.col.size());
+    if (getenv("CPK_VERBOSE"))
+        fprintf(stderr, "[cpk] set-up ms: parse+levels %.2f, sweeps %.2f, K_P SELL %.2f, uploads+stream %.2f\n",
+                t_parse, t_sweeps - t_parse, t_sell - t_sweeps, ms_since(t_begin) - t_sell);
+    if (getenv("CPK_VERBOSE")) {
+        // item shapes per direction: width (entries per lane) histogram, warp-rows counted apart
+        for (int dir = 0; dir < 2; ++dir) {
+            long long hist[10] = {0}, wr = 0, rows = 0;
+            for (int t = dir ? W.nfwd : 0; t < (dir ? W.nitems : W.nfwd); ++t) {
+                const int wdt = (W.sptr[t + 1] - W.sptr[t]) / 32;
+                if (W.flags[(size_t)t * 32] & F_WARPROW) { ++wr; continue; }
+                hist[std::min(wdt, 9)]++;
+                for (int l = 0; l < 32; ++l) rows += W.rid[(size_t)t * 32 + l] >= 0;
+            }
+            fprintf(stderr, "[cpk]   %s items by width 0..8,9+: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld; warp-rows %lld; rows in lane items %lld\n",
+                    dir ? "bwd" : "fwd", hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7], hist[8], hist[9], wr, rows);
+        }
+    }
     if (getenv("CPK_VERBOSE") && m.cw.nblk)
         fprintf(stderr, "[cpk] compact walk: %d blocks of %d B, %lld levels in %lld steps, %lld items, shared memory %zu B\n",
                 m.cw.nblk, kCwBlock, cws.n_levels, cws.n_steps, cws.n_items, cw_smem_bytes(N));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));      // uploads done (pageable sources are still alive here)
     *out = register_obj(std::move(o));
     return CPK_OK;
 }
@@ -1587,6 +1629,7 @@ int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_h
     CUDA_TRY(o->ar.alloc(&o->d_status, 1, true));
     CUDA_TRY(o->ar.alloc(&o->d_b, d.N));
     CUDA_TRY(o->ar.alloc(&o->d_x, d.N));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
     M->in_system = true;
     *out = register_obj(std::move(o));
     return CPK_OK;
@@ -1675,6 +1718,7 @@ static int ensure_buffers(System *S, const Plan &p, int64_t hist_cap)
         CUDA_TRY(S->war.alloc(&S->d_work, (size_t)S->work_len));
         CUDA_TRY(S->war.alloc(&S->d_hist, (size_t)S->hist_cap));
         CUDA_TRY(S->war.alloc(&S->d_gs, (size_t)std::max<long long>(S->gs_len, 1)));
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));   // the launch stream does not wait for the legacy stream
     }
     return CPK_OK;
 }
