@@ -10,10 +10,10 @@ iteration happens in libcpk_b200.so on the GPU; there is no CPU fallback.
 """
 from .operators import opLDL2, KktSystem                      # noqa: F401
 from .solvers import (cpcg, cpcglanczos, cpminres, cpsymmlq, cpgmres, cpdqgmres,   # noqa: F401
-                      reg_cpkrylov, SolverError, SOLVERS)
+                      reg_cpkrylov, reg_solve_on, SolverError, SOLVERS)
 from ._lib import CpkError, CpkLibraryMissing, LIB_PATH     # noqa: F401
 from .matio import load_mat_system, system_from_K, solve_sequence   # noqa: F401
 
 __all__ = ["opLDL2", "KktSystem", "cpcg", "cpcglanczos", "cpminres", "cpsymmlq", "cpgmres",
-           "cpdqgmres", "reg_cpkrylov", "SolverError", "SOLVERS", "CpkError", "CpkLibraryMissing",
+           "cpdqgmres", "reg_cpkrylov", "reg_solve_on", "SolverError", "SOLVERS", "CpkError", "CpkLibraryMissing",
            "load_mat_system", "system_from_K", "solve_sequence"]

@@ -79,7 +79,11 @@ API = [
     ("cpk_ldl2_apply", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, _PSTATS]),
     ("cpk_ldl2_matvec", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, _PSTATS]),
     ("cpk_ldl2_info", C.c_int, [_H] + [C.POINTER(C.c_int64)] * 4),
+    ("cpk_ldl2_create_sqd", C.c_int, [C.POINTER(_H), _PCSC, _PCSC, _PCSC, C.POINTER(C.c_int64), C.c_int]),
+    ("cpk_ldl2_refactor", C.c_int, [_H, _PCSC, _PCSC, _PCSC]),
+    ("cpk_ldl2_get_factor", C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _PD, _PD]),
     ("cpk_system_create", C.c_int, [C.POINTER(_H), _PCSC, _PCSC, _H]),
+    ("cpk_system_update", C.c_int, [_H, _PCSC, _PCSC]),
     ("cpk_system_matvec", C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, _PSTATS]),
     ("cpk_opts_default", None, [_POPTS, C.c_int, C.c_int64, C.c_int64]),
     ("cpk_solve", C.c_int, [_H, C.c_int, C.c_void_p, _POPTS, C.c_void_p, C.c_void_p, C.c_int, _PSTATS, C.c_void_p, C.c_int64]),

@@ -736,7 +736,11 @@ struct Ldl2 : Object {
     double *d_z = nullptr, *d_y = nullptr;
     DevStatus *d_status = nullptr;
     bool in_system = false;
+    // device-side numeric factorization (cpk_ldl2_create_sqd / cpk_ldl2_refactor)
+    std::unique_ptr<struct SqdPlan> plan;
+    bool sweep_stale = false;           // after a refactorization only the compact stream holds the new factor
     Ldl2() { kind = OBJ_LDL2; }
+    ~Ldl2();
 };
 
 struct System : Object {
@@ -990,6 +994,176 @@ extern "C" int cpk_debug_barrier_cycles(int device, int iters, double *sync_cycl
 }
 
 // ===========================================================================
+// Numeric LDL' on the device for symmetric quasi-definite K_P with a STATIC
+// permutation (a sequence of interior-point systems keeps
+// its pattern, opLDL2.m:81-82 re-assembles and re-factors each of them from scratch).
+// Quasi-definite matrices are strongly factorizable: every symmetric permutation has
+// an LDL' factorization with a diagonal D, so the permutation is chosen once for
+// fill and the numeric work is a fixed dependency graph:
+//     d_k  = a_kk - sum_j L_kj^2 d_j
+//     L_ik = (a_ik - sum_j L_ij d_j L_kj) / d_k          (j < k, both factors nonzero)
+// The host compiles that graph once per pattern ("plan"): every entry of L and D is a
+// node with its list of triple products, nodes are sorted into dependency levels, and
+// one CTA evaluates level after level.  The plan also records where every value sits
+// in the compact-walk stream, so a refactorization rewrites the operator in place.
+// ===========================================================================
+struct SqdPlan {
+    int N = 0;
+    int64_t nnzL = 0, ne = 0, nops = 0, nvals_in = 0;
+    int nlev = 0;
+    std::vector<int64_t> colptr, rowind;    // strict lower triangle of L, CSC (symbolic pattern incl. fill)
+    int64_t nnzA = 0, nnzB = 0, nnzC = 0;   // lengths of the value arrays a refactorization must bring
+    // device copies
+    DevArena ar;
+    double *d_fval = nullptr, *d_vals_in = nullptr;
+    const int *d_asrc = nullptr, *d_dk = nullptr, *d_exec = nullptr, *d_levptr = nullptr, *d_opptr = nullptr, *d_ops = nullptr;
+    const int *d_spos = nullptr, *d_ssrc = nullptr;
+    int64_t ns = 0;
+};
+Ldl2::~Ldl2() {}
+
+struct SqdHost {
+    std::vector<int> asrc, dk, exec, levptr, opptr, ops;
+};
+
+// symbolic analysis + plan.  K_P = [A B'; B C] (blocks as handed to cpk_ldl2_create), perm[k] =
+// original index of row k of the permuted matrix.
+static int sqd_plan(const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int N, int nA,
+                    SqdPlan *P, SqdHost *H)
+{
+    std::vector<int> invp(N, -1);
+    for (int k = 0; k < N; ++k) {
+        if (perm[k] < 0 || perm[k] >= N || invp[perm[k]] >= 0) return fail(CPK_ERR_ARG, "perm is not a permutation of 0..N-1");
+        invp[perm[k]] = k;
+    }
+    // lower triangle of P' K_P P by columns: (row, index into the concatenated values [A | B | C])
+    std::vector<std::vector<std::pair<int, int>>> low(N);
+    std::vector<int> diagsrc(N, -1);
+    int64_t base = 0;
+    auto add = [&](int64_t r, int64_t c, int64_t src, bool mirror_ok) {
+        int pr = invp[r], pc = invp[c];
+        if (pr < pc) { if (!mirror_ok) return; std::swap(pr, pc); }       // A and C bring both triangles, B only one
+        if (pr == pc) { if (diagsrc[pc] < 0) diagsrc[pc] = (int)src; }
+        else low[pc].emplace_back(pr, (int)src);
+    };
+    for (int64_t j = 0; j < A->ncols; ++j) for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; ++k) add(A->rowind[k], j, base + k, false);
+    base += A->colptr[A->ncols];
+    for (int64_t j = 0; j < B->ncols; ++j) for (int64_t k = B->colptr[j]; k < B->colptr[j + 1]; ++k) add(nA + B->rowind[k], j, base + k, true);
+    base += B->colptr[B->ncols];
+    for (int64_t j = 0; j < C->ncols; ++j) for (int64_t k = C->colptr[j]; k < C->colptr[j + 1]; ++k) add(nA + C->rowind[k], nA + j, base + k, false);
+    base += C->colptr[C->ncols];
+    P->nvals_in = base;
+    P->nnzA = A->colptr[A->ncols]; P->nnzB = B->colptr[B->ncols]; P->nnzC = C->colptr[C->ncols];
+    for (int k = 0; k < N; ++k) if (diagsrc[k] < 0) return fail(CPK_ERR_ARG, "K_P has a structurally zero diagonal entry (row %lld): not quasi-definite", (long long)perm[k]);
+    // column structures with fill (elimination tree: parent = first off-diagonal row)
+    std::vector<std::vector<int>> st(N), children(N);
+    std::vector<int> mark(N, -1);
+    for (int k = 0; k < N; ++k) {
+        std::vector<int> &sk = st[k];
+        for (auto &e : low[k]) if (mark[e.first] != k) { mark[e.first] = k; sk.push_back(e.first); }
+        for (int c : children[k]) for (int i : st[c]) if (i != k && mark[i] != k) { mark[i] = k; sk.push_back(i); }
+        std::sort(sk.begin(), sk.end());
+        if (!sk.empty()) children[sk[0]].push_back(k);
+    }
+    P->N = N;
+    P->colptr.assign(N + 1, 0);
+    for (int k = 0; k < N; ++k) P->colptr[k + 1] = P->colptr[k] + (int64_t)st[k].size();
+    P->nnzL = P->colptr[N];
+    P->ne = P->nnzL + N;
+    if (P->ne >= INT32_MAX / 2) return fail(CPK_ERR_UNSUPPORTED, "factor too large for the device factorization plan");
+    P->rowind.resize(P->nnzL);
+    for (int k = 0; k < N; ++k) std::copy(st[k].begin(), st[k].end(), P->rowind.begin() + P->colptr[k]);
+    const int ne = (int)P->ne, nnzL = (int)P->nnzL;
+    auto id_of = [&](int i, int k) -> int {         // entry (i,k), i > k
+        const auto &sk = st[k];
+        return (int)(P->colptr[k] + (std::lower_bound(sk.begin(), sk.end(), i) - sk.begin()));
+    };
+    H->asrc.assign(ne, -1);
+    H->dk.assign(ne, -1);
+    for (int k = 0; k < N; ++k) {
+        H->asrc[nnzL + k] = diagsrc[k];
+        for (auto &e : low[k]) { const int id = id_of(e.first, k); if (H->asrc[id] < 0) H->asrc[id] = e.second; }
+        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) H->dk[q] = nnzL + k;
+    }
+    // rows of L: (column j, entry id) with j ascending
+    std::vector<std::vector<std::pair<int, int>>> rowc(N);
+    for (int j = 0; j < N; ++j) for (int64_t q = P->colptr[j]; q < P->colptr[j + 1]; ++q) rowc[P->rowind[q]].emplace_back(j, (int)q);
+    // triple products of every node, j ascending
+    std::vector<int> lev(ne, 0), pos(N, -1);
+    std::vector<std::vector<int>> opl(ne);
+    int64_t nops = 0;
+    for (int k = 0; k < N; ++k) {
+        pos[k] = nnzL + k;
+        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) pos[P->rowind[q]] = (int)q;
+        for (auto &kj : rowc[k]) {
+            const int j = kj.first, id_kj = kj.second;
+            const auto &sj = st[j];
+            for (size_t t = std::lower_bound(sj.begin(), sj.end(), k) - sj.begin(); t < sj.size(); ++t) {
+                const int i = sj[t];
+                const int id_ij = (int)(P->colptr[j] + t);
+                if (i != k && (pos[i] < P->colptr[k] || pos[i] >= P->colptr[k + 1]))
+                    return fail(CPK_ERR_ARG, "internal: fill pattern is not closed (column %d, row %d)", k, i);
+                std::vector<int> &o = opl[pos[i]];
+                o.push_back(id_ij); o.push_back(id_kj); o.push_back(nnzL + j);
+                ++nops;
+            }
+        }
+        if (nops > 60000000) return fail(CPK_ERR_UNSUPPORTED, "device factorization plan exceeds 6e7 products: keep the host factorization for this system");
+        // levels: the diagonal node first, then the column below it
+        int l = 0;
+        for (size_t t = 0; t < opl[nnzL + k].size(); t += 3) l = std::max(l, lev[opl[nnzL + k][t]] + 1);
+        lev[nnzL + k] = l;
+        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) {
+            int lq = l + 1;
+            for (size_t t = 0; t < opl[q].size(); t += 3) lq = std::max(lq, std::max(lev[opl[q][t]], lev[opl[q][t + 1]]) + 1);
+            lev[q] = lq;
+        }
+    }
+    P->nops = nops;
+    int nlev = 0;
+    for (int e = 0; e < ne; ++e) nlev = std::max(nlev, lev[e] + 1);
+    P->nlev = nlev;
+    H->levptr.assign(nlev + 1, 0);
+    for (int e = 0; e < ne; ++e) H->levptr[lev[e] + 1]++;
+    for (int l = 0; l < nlev; ++l) H->levptr[l + 1] += H->levptr[l];
+    H->exec.resize(ne);
+    {
+        std::vector<int> nxt(H->levptr.begin(), H->levptr.end() - 1);
+        for (int e = 0; e < ne; ++e) H->exec[nxt[lev[e]]++] = e;
+    }
+    H->opptr.assign(ne + 1, 0);
+    for (int e = 0; e < ne; ++e) H->opptr[e + 1] = H->opptr[e] + (int)(opl[e].size() / 3);
+    H->ops.resize((size_t)3 * nops);
+    for (int e = 0; e < ne; ++e) std::copy(opl[e].begin(), opl[e].end(), H->ops.begin() + (size_t)3 * H->opptr[e]);
+    return CPK_OK;
+}
+
+// one CTA: node values from the new matrix entries, then level after level, then the scatter
+// of the factor into the compact-walk stream (ns = 0: no scatter)
+__global__ void __launch_bounds__(kBlock, 1)
+k_sqd_factor(int ne, int nlev, const double *vals_in, const int *asrc, const int *dk, const int *exec, const int *levptr,
+             const int *opptr, const int *ops, double *fval, int ns, const int *spos, const int *ssrc, double *stream, int *bad)
+{
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) fval[e] = asrc[e] >= 0 ? vals_in[asrc[e]] : 0.0;
+    __syncthreads();
+    for (int l = 0; l < nlev; ++l) {
+        const int a = levptr[l], b = levptr[l + 1];
+        for (int q = a + (int)threadIdx.x; q < b; q += blockDim.x) {
+            const int e = exec[q];
+            double v = fval[e];
+            for (int t = opptr[e]; t < opptr[e + 1]; ++t)
+                v = v - (fval[ops[3 * t]] * fval[ops[3 * t + 2]]) * fval[ops[3 * t + 1]];      // L_ij d_j L_kj
+            const int d = dk[e];
+            if (d >= 0) v = v / fval[d];
+            else if (v == 0.0 || v != v) atomicExch(bad, e + 1);        // zero or NaN pivot
+            fval[e] = v;
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < ns; t += blockDim.x) stream[spos[t]] = fval[ssrc[t]];
+}
+
+// ===========================================================================
 // C ABI
 // ===========================================================================
 // (C linkage comes from the declarations in cpk_b200.h)
@@ -1096,6 +1270,8 @@ static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, in
 }
 
 // ---------------------------------------------------------------------------
+static thread_local bool g_force_compact = false;   // set by cpk_ldl2_create_sqd around its call of cpk_ldl2_create
+
 int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
                     const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
 {
@@ -1149,8 +1325,9 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // (a solver scratch too large for the stream's shared memory): no tail inversion for it,
     // which is most of the host-side set-up time of a small system
     const char *cenv = getenv("CPK_LDL_COMPACT");
-    const bool compact_walk = !use_grid(N) && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)) &&
-                              cw_smem_bytes(N) <= (size_t)dc->max_dsm;
+    const bool compact_walk = g_force_compact ||
+                              (!use_grid(N) && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)) &&
+                               cw_smem_bytes(N) <= (size_t)dc->max_dsm);
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
@@ -1407,6 +1584,249 @@ extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int
     return CPK_OK;
 }
 
+// positions (in doubles) of every factor value inside a compact-walk stream, read off a twin
+// stream that was built from the same pattern with "value = node id + 1"
+static void cw_value_map(const std::vector<unsigned char> &ids, std::vector<int> &spos, std::vector<int> &ssrc)
+{
+    const size_t nblk = ids.size() / kCwBlock;
+    auto take = [&](size_t byte) {
+        double idv;
+        memcpy(&idv, ids.data() + byte, 8);
+        if (idv != 0.0) { spos.push_back((int)(byte / 8)); ssrc.push_back((int)idv - 1); }
+    };
+    for (size_t b = 0; b < nblk; ++b) {
+        const unsigned char *blk = ids.data() + b * kCwBlock;
+        const int nsteps = *reinterpret_cast<const int *>(blk);
+        const int *slot = reinterpret_cast<const int *>(blk + 16);
+        std::vector<int> seen;              // D chunks are shared by the 16 slots of their step
+        for (int t = 0; t < nsteps * kWarpsPerCta; ++t) {
+            const int off = slot[4 * t], y = slot[4 * t + 1];
+            const int kind = y & 15, width = (y >> 8) & 0xffff, stride = (y >> 24) & 0xff;
+            if (kind == 0) continue;
+            const size_t base = b * kCwBlock + (size_t)off;
+            if (kind == CW_DCHUNK) {
+                if (std::find(seen.begin(), seen.end(), off) != seen.end()) continue;
+                seen.push_back(off);
+                for (int r = 0; r < width; ++r) take(base + 8 * (size_t)r);
+            } else if (kind == CW_ROWS2) {
+                for (int q = 0; q < stride; ++q) { take(base + 32 * (size_t)q + 16); take(base + 32 * (size_t)q + 24); }
+            } else {
+                const size_t v0 = base + (kind == CW_ROWS ? 4 * (size_t)stride : 0);
+                for (int q = 0; q < width * stride; ++q) take(v0 + 8 * (size_t)q);
+            }
+        }
+    }
+}
+
+static int sqd_launch(DeviceCtx *dc, SqdPlan *P, double *stream)
+{
+    int *d_bad = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_bad, sizeof(int), dc->stream));
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), dc->stream));
+    const int ns = stream ? (int)P->ns : 0;
+    k_sqd_factor<<<1, kBlock, 0, dc->stream>>>((int)P->ne, P->nlev, P->d_vals_in, P->d_asrc, P->d_dk, P->d_exec, P->d_levptr, P->d_opptr,
+                                                P->d_ops, P->d_fval, ns, P->d_spos, P->d_ssrc, stream, d_bad);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    cudaFreeAsync(d_bad, dc->stream);
+    if (bad) return fail(CPK_ERR_BREAKDOWN, "device LDL': zero or NaN pivot at row %d of the permuted matrix (K_P is not quasi-definite?)",
+                         bad - 1 - (int)P->nnzL);
+    return CPK_OK;
+}
+
+static int sqd_upload_values(DeviceCtx *dc, SqdPlan *P, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
+{
+    if (A->colptr[A->ncols] != P->nnzA || B->colptr[B->ncols] != P->nnzB || C->colptr[C->ncols] != P->nnzC)
+        return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
+    std::vector<double> v((size_t)P->nvals_in);
+    if (P->nnzA) memcpy(v.data(), A->val, sizeof(double) * P->nnzA);
+    if (P->nnzB) memcpy(v.data() + P->nnzA, B->val, sizeof(double) * P->nnzB);
+    if (P->nnzC) memcpy(v.data() + P->nnzA + P->nnzB, C->val, sizeof(double) * P->nnzC);
+    CUDA_TRY(cudaMemcpyAsync(P->d_vals_in, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    return CPK_OK;
+}
+
+int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int device)
+{
+    if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create_sqd: null output handle");
+    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !perm) return fail(CPK_ERR_ARG, "Invalid number of arguments.");
+    if (A->nrows != A->ncols || C->nrows != C->ncols) return fail(CPK_ERR_DIM, "First and last arguments must be square.");
+    if (B->ncols != A->nrows || B->nrows != C->nrows) return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    const int64_t N64 = A->nrows + C->nrows;
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+    if (N64 >= INT32_MAX || use_grid((int)N64) || cw_smem_bytes((int)N64) > (size_t)dc->max_dsm)
+        return fail(CPK_ERR_UNSUPPORTED, "device factorization serves the one-CTA team (N <= ~11000); larger systems bring host factors to cpk_ldl2_create");
+    const int N = (int)N64, nA = (int)A->nrows;
+    CUDA_TRY(cudaSetDevice(device));
+    auto P = std::make_unique<SqdPlan>();
+    P->ar.device = device;
+    SqdHost H;
+    rc = sqd_plan(A, B, C, perm, N, nA, P.get(), &H);
+    if (rc) return rc;
+    CUDA_TRY(P->ar.alloc(&P->d_fval, (size_t)P->ne));
+    CUDA_TRY(P->ar.alloc(&P->d_vals_in, (size_t)P->nvals_in));
+    CUDA_TRY(P->ar.upload(&P->d_asrc, H.asrc));
+    CUDA_TRY(P->ar.upload(&P->d_dk, H.dk));
+    CUDA_TRY(P->ar.upload(&P->d_exec, H.exec));
+    CUDA_TRY(P->ar.upload(&P->d_levptr, H.levptr));
+    CUDA_TRY(P->ar.upload(&P->d_opptr, H.opptr));
+    CUDA_TRY(P->ar.upload(&P->d_ops, H.ops));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+    rc = sqd_upload_values(dc, P.get(), A, B, C);
+    if (rc) return rc;
+    rc = sqd_launch(dc, P.get(), nullptr);
+    if (rc) return rc;
+    // factor back to the host once: the regular create builds every structure from it
+    std::vector<double> fval((size_t)P->ne);
+    CUDA_TRY(cudaMemcpy(fval.data(), P->d_fval, sizeof(double) * fval.size(), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> dptr(N + 1), dind(N);
+    for (int i = 0; i <= N; ++i) dptr[i] = i;
+    for (int i = 0; i < N; ++i) dind[i] = i;
+    cpk_csc Lc{N, N, P->colptr.data(), P->rowind.data(), fval.data()};
+    cpk_csc Dc{N, N, dptr.data(), dind.data(), fval.data() + P->nnzL};
+    cpk_handle h = 0;
+    g_force_compact = true;
+    rc = cpk_ldl2_create(&h, A, B, C, &Lc, &Dc, perm, device);
+    g_force_compact = false;
+    if (rc) return rc;
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M || M->d.cw.nblk == 0) { cpk_destroy(h); return fail(CPK_ERR_UNSUPPORTED, "device factorization needs the compact walk"); }
+    // where every node value sits in the stream: twin stream built with ids as values
+    {
+        std::vector<double> idv((size_t)P->ne);
+        for (int64_t e = 0; e < P->ne; ++e) idv[e] = (double)(e + 1);
+        cpk_csc Li{N, N, P->colptr.data(), P->rowind.data(), idv.data()};
+        cpk_csc Di{N, N, dptr.data(), dind.data(), idv.data() + P->nnzL};
+        HostLdl HL;
+        rc = parse_ldl(&Li, &Di, perm, N, &HL);
+        if (rc) { cpk_destroy(h); return rc; }
+        CwStream ids;
+        cw_sweep(ids, N, HL.Lrows, HL.lf, HL.nlf, 0, 0);
+        cw_dpass(ids, N, HL.d, HL.e, HL.partner);
+        cw_sweep(ids, N, HL.Lcols, HL.lb, HL.nlb, N, N);
+        ids.flush();
+        if ((int)(ids.bytes.size() / kCwBlock) != M->d.cw.nblk) { cpk_destroy(h); return fail(CPK_ERR_ARG, "internal: twin stream differs in size"); }
+        std::vector<int> spos, ssrc;
+        cw_value_map(ids.bytes, spos, ssrc);
+        if ((int64_t)spos.size() != 2 * P->nnzL + N) { cpk_destroy(h); return fail(CPK_ERR_ARG, "internal: stream holds %zu factor values, expected %lld", spos.size(), (long long)(2 * P->nnzL + N)); }
+        P->ns = (int64_t)spos.size();
+        CUDA_TRY(P->ar.upload(&P->d_spos, spos));
+        CUDA_TRY(P->ar.upload(&P->d_ssrc, ssrc));
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+    }
+    M->plan = std::move(P);
+    *out = h;
+    return CPK_OK;
+}
+
+// new values, same patterns: numeric factorization on the device, written into the operator in place
+int cpk_ldl2_refactor(cpk_handle h, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "cpk_ldl2_refactor: not an opLDL2 handle");
+    if (!M->plan) return fail(CPK_ERR_ARG, "cpk_ldl2_refactor: the operator was not created by cpk_ldl2_create_sqd");
+    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C)) return fail(CPK_ERR_ARG, "Invalid number of arguments.");
+    if (A->nrows != M->d.nA || A->ncols != M->d.nA || C->nrows != M->d.nC || C->ncols != M->d.nC || B->nrows != M->d.nC || B->ncols != M->d.nA)
+        return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    DeviceCtx *dc;
+    int rc = get_device_ctx(M->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(M->device));
+    rc = sqd_upload_values(dc, M->plan.get(), A, B, C);
+    if (rc) return rc;
+    rc = sqd_launch(dc, M->plan.get(), reinterpret_cast<double *>(const_cast<unsigned char *>(M->d.cw.stream)));
+    if (rc) return rc;
+    M->sweep_stale = true;
+    // K_P, B', C for the refinement residual and the residual update: same layout, new values
+    const int nA = M->d.nA, nC = M->d.nC;
+    HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
+    HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, nA, nC);
+    const HSell hs[3] = {build_sell(KP), build_sell(Bt), build_sell(Cr)};
+    const DevSell *ds[3] = {&M->d.KP, &M->d.K12, &M->d.K22};
+    for (int q = 0; q < 3; ++q) {
+        if (hs[q].nslices != ds[q]->nslices || (int)hs[q].lrow.size() != ds[q]->nlong)
+            return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
+        if (!hs[q].val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->val), hs[q].val.data(), sizeof(double) * hs[q].val.size(), cudaMemcpyHostToDevice, dc->stream));
+        if (!hs[q].lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->lval), hs[q].lval.data(), sizeof(double) * hs[q].lval.size(), cudaMemcpyHostToDevice, dc->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    return CPK_OK;
+}
+
+// pattern (strict lower triangle, CSC) and values of the factor held on the device
+int cpk_ldl2_get_factor(cpk_handle h, int64_t *nnz, int64_t *colptr, int64_t *rowind, double *Lval, double *d)
+{
+    Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
+    if (!M || !M->plan) return fail(CPK_ERR_ARG, "cpk_ldl2_get_factor: the operator was not created by cpk_ldl2_create_sqd");
+    SqdPlan *P = M->plan.get();
+    if (nnz) *nnz = P->nnzL;
+    if (colptr) std::copy(P->colptr.begin(), P->colptr.end(), colptr);
+    if (rowind) std::copy(P->rowind.begin(), P->rowind.end(), rowind);
+    CUDA_TRY(cudaSetDevice(M->device));
+    if (Lval && P->nnzL) CUDA_TRY(cudaMemcpy(Lval, P->d_fval, sizeof(double) * P->nnzL, cudaMemcpyDeviceToHost));
+    if (d) CUDA_TRY(cudaMemcpy(d, P->d_fval + P->nnzL, sizeof(double) * P->N, cudaMemcpyDeviceToHost));
+    return CPK_OK;
+}
+
+// new values of H and C (same patterns) for the mat-vecs of the solver loops
+int cpk_system_update(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
+{
+    System *S = lookup<System>(h, OBJ_SYSTEM);
+    if (!S) return fail(CPK_ERR_ARG, "cpk_system_update: not a system handle");
+    if (!csc_ok(A) || !csc_ok(C)) return fail(CPK_ERR_ARG, "cpk_system_update: bad matrix");
+    const int n = S->h.n, m = S->h.m;
+    if (A->nrows != n || A->ncols != n || C->nrows != m || C->ncols != m) return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    DeviceCtx *dc;
+    int rc = get_device_ctx(S->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(S->device));
+    HCsr Hr = csr_from_csc(*A), Cr = csr_from_csc(*C);
+    HSell s;
+    s.nrows = n + m; s.ncols = n + m;
+    sell_append(s, Hr, 0, n, 0, 0);
+    sell_append(s, Cr, 0, m, n, n);
+    HSell sc = build_sell(Cr);
+    const HSell *hs[2] = {&s, &sc};
+    const DevSell *ds[2] = {&S->h.HC, &S->h.Cm};
+    for (int q = 0; q < 2; ++q) {
+        if (hs[q]->nslices != ds[q]->nslices || (int)hs[q]->lrow.size() != ds[q]->nlong)
+            return fail(CPK_ERR_DIM, "cpk_system_update needs the sparsity pattern the system was created with");
+        if (!hs[q]->val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->val), hs[q]->val.data(), sizeof(double) * hs[q]->val.size(), cudaMemcpyHostToDevice, dc->stream));
+        if (!hs[q]->lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->lval), hs[q]->lval.data(), sizeof(double) * hs[q]->lval.size(), cudaMemcpyHostToDevice, dc->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    return CPK_OK;
+}
+
+// debug / test hook (no device needed): the factorization plan of cpk_ldl2_create_sqd.
+// sizes = {ne, nnzL, nops, nlev, nvals_in}; call with the arrays NULL to get the sizes.
+extern "C" int cpk_debug_sqd_plan(const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int64_t *sizes,
+                                  int64_t *colptr, int64_t *rowind, int *asrc, int *dk, int *exec, int *levptr, int *opptr, int *ops)
+{
+    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !perm || !sizes) return fail(CPK_ERR_ARG, "cpk_debug_sqd_plan: bad argument");
+    const int N = (int)(A->nrows + C->nrows);
+    SqdPlan P;
+    SqdHost H;
+    int rc = sqd_plan(A, B, C, perm, N, (int)A->nrows, &P, &H);
+    if (rc) return rc;
+    sizes[0] = P.ne; sizes[1] = P.nnzL; sizes[2] = P.nops; sizes[3] = P.nlev; sizes[4] = P.nvals_in;
+    if (colptr) std::copy(P.colptr.begin(), P.colptr.end(), colptr);
+    if (rowind) std::copy(P.rowind.begin(), P.rowind.end(), rowind);
+    if (asrc) std::copy(H.asrc.begin(), H.asrc.end(), asrc);
+    if (dk) std::copy(H.dk.begin(), H.dk.end(), dk);
+    if (exec) std::copy(H.exec.begin(), H.exec.end(), exec);
+    if (levptr) std::copy(H.levptr.begin(), H.levptr.end(), levptr);
+    if (opptr) std::copy(H.opptr.begin(), H.opptr.end(), opptr);
+    if (ops) std::copy(H.ops.begin(), H.ops.end(), ops);
+    return CPK_OK;
+}
+
 static int ldl2_set(cpk_handle h, int which, double v)
 {
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
@@ -1537,6 +1957,7 @@ int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_st
     const DevSystem *ps = M->d_sys_alone;
     size_t dsm = 0;
     int cw_off = cw_place(dc, M->d, use_grid(N), 0, &dsm);
+    if (M->sweep_stale && cw_off < 0) return fail(CPK_ERR_UNSUPPORTED, "a refactorized operator only lives in the compact-walk stream, which does not fit this launch");
     void *params[] = {(void *)&ps, (void *)&dz, (void *)&dy, (void *)&d_st, (void *)&dc->ctl, (void *)&dc->partials, (void *)&cw_off};
     float ms = 0.f;
     rc = launch_team(dc, use_grid(N), k_apply<true>, k_apply<false>, params, dsm, &ms);
@@ -1762,6 +2183,7 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     a.hist = S->d_hist; a.hist_cap = cap; a.gs = S->d_gs; a.status = S->d_status;
     size_t dsm_total = plan.dsm;
     a.cw_off = cw_place(dc, S->h.M, grid, plan.dsm, &dsm_total);
+    if (S->M->sweep_stale && a.cw_off < 0) return fail(CPK_ERR_UNSUPPORTED, "a refactorized operator only lives in the compact-walk stream, which does not fit next to this solver's shared-memory scratch");
     CUDA_TRY(cudaMemcpyAsync(S->d_args, &a, sizeof a, cudaMemcpyHostToDevice, dc->stream));
     CUDA_TRY(cudaMemsetAsync(S->d_status, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = S->d_sys; const SolveArgs *pa = S->d_args;
@@ -1903,6 +2325,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         a.hist = want_hist ? dc->d_stage + 2 * tot + (size_t)i * 3 * cap : S->d_hist;
         a.hist_cap = cap; a.gs = S->d_gs; a.status = dc->d_bstatus + i;
         a.cw_off = q < n_cta ? cw_place(dc, S->h.M, false, plan.dsm, &dsm_total) : -1;
+        if (S->M->sweep_stale && a.cw_off < 0) return fail(CPK_ERR_UNSUPPORTED, "batch entry %lld: a refactorized operator only lives in the compact-walk stream, which does not fit this launch", (long long)i);
         hargs[q] = a;
     }
     CUDA_TRY(cudaMemcpyAsync(db, hb, sizeof(double) * tot, cudaMemcpyHostToDevice, dc->stream));

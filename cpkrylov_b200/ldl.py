@@ -70,3 +70,11 @@ def ldl_factor(K, method="auto"):
     if method == "dense_bk":
         return ldl_dense_bk(K)
     raise ValueError("unknown LDL method %r" % (method,))
+
+
+def static_perm(K):
+    """Fill-reducing symmetric permutation for the device factorization of a symmetric
+    quasi-definite matrix (``opLDL2(..., factors="device", perm=...)``): the ordering a
+    SuperLU symmetric-mode factorization of the pattern chooses (MMD on A'+A).  It depends on
+    the pattern only, so one call serves a whole sequence.  perm[k] = original index of row k."""
+    return ldl_superlu(K, check=False)[3]

@@ -33,7 +33,7 @@ class opLDL2:
     uploads everything once.  ``M @ z`` / ``M * z`` runs on the GPU.
     """
 
-    def __init__(self, A, B, C, factors=None, ldl_method="auto", device=0):
+    def __init__(self, A, B, C, factors=None, ldl_method="auto", device=0, perm=None):
         A = sp.csc_matrix(A); B = sp.csc_matrix(B); C_ = sp.csc_matrix(C)
         nA, nC = A.shape[0], C_.shape[0]
         if nA != A.shape[1] or nC != C_.shape[1]:
@@ -43,6 +43,28 @@ class opLDL2:
         self.nA, self.nC, self.n = nA, nC, nA + nC
         self.shape = (self.n, self.n)
         t0 = time.perf_counter()
+        if isinstance(factors, str) and factors == "device":
+            # symmetric quasi-definite K_P, static permutation: numeric LDL' on the device
+            # (cpk_ldl2_create_sqd); `refactor` then serves the next systems of the sequence
+            if perm is None:
+                raise ValueError("factors='device' needs the fill-reducing permutation `perm` "
+                                 "(e.g. cpkrylov_b200.ldl.static_perm(K_P))")
+            self.t_factor = 0.0
+            self.factors = None
+            perm = np.ascontiguousarray(perm, dtype=np.int64)
+            keep = [_lib.Csc(A), _lib.Csc(B), _lib.Csc(C_)]
+            h = ct.c_uint64(0)
+            _lib.check(_lib.lib().cpk_ldl2_create_sqd(ct.byref(h), *[k.ref() for k in keep],
+                                                      perm.ctypes.data_as(ct.POINTER(ct.c_int64)), int(device)))
+            self.t_upload = time.perf_counter() - t0
+            self.handle = h
+            self.device = device
+            self._owned_by_system = False
+            self._keep = None
+            self._nitref, self._itref_tol, self._force_itref, self._residual_update = 3, 1.0e-8, False, False
+            self._ru_stateful = False
+            self.last_stats = None
+            return
         if factors is None:
             K = sp.bmat([[A, B.T], [B, C_]], format="csc")                       # opLDL2.m:81
             factors = ldl_factor(K, ldl_method)                                  # opLDL2.m:82
@@ -173,6 +195,29 @@ class opLDL2:
             e[i] = 0.0
         return X
 
+    # -- sequences with a fixed pattern ---------------
+    def refactor(self, A, B, C):
+        """New values, same sparsity patterns: numeric LDL' on the device, in place.
+        Only for operators created with ``factors="device"``."""
+        keep = [_lib.Csc(sp.csc_matrix(A)), _lib.Csc(sp.csc_matrix(B)), _lib.Csc(sp.csc_matrix(C))]
+        t0 = time.perf_counter()
+        _lib.check(_lib.lib().cpk_ldl2_refactor(self.handle, *[k.ref() for k in keep]))
+        self.t_refactor = time.perf_counter() - t0
+
+    def device_factor(self):
+        """(L, d): unit lower triangular L (CSC, pattern with fill) and diag(D) as the device holds them."""
+        L_ = _lib.lib()
+        nnz = ct.c_int64(0)
+        _lib.check(L_.cpk_ldl2_get_factor(self.handle, ct.byref(nnz), None, None, None, None))
+        N = self.n
+        colptr = np.zeros(N + 1, dtype=np.int64); rowind = np.zeros(max(nnz.value, 1), dtype=np.int64)
+        val = np.zeros(max(nnz.value, 1)); d = np.zeros(N)
+        _lib.check(L_.cpk_ldl2_get_factor(self.handle, ct.byref(nnz), colptr.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                                          rowind.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                                          val.ctypes.data_as(ct.POINTER(ct.c_double)), d.ctypes.data_as(ct.POINTER(ct.c_double))))
+        L = sp.csc_matrix((val[:nnz.value], rowind[:nnz.value], colptr), shape=(N, N)) + sp.identity(N, format="csc")
+        return L, d
+
     def close(self):
         if getattr(self, "handle", None) is not None and not self._owned_by_system:
             try:
@@ -203,6 +248,11 @@ class KktSystem:
         _lib.check(_lib.lib().cpk_system_create(ct.byref(h), a.ref(), c.ref(), M.handle))
         self.handle = h
         M._owned_by_system = True
+
+    def update(self, A, Cm):
+        """New values of A (= H) and C, same patterns (next system of a sequence)."""
+        a, c = _lib.Csc(sp.csc_matrix(A)), _lib.Csc(sp.csc_matrix(Cm))
+        _lib.check(_lib.lib().cpk_system_update(self.handle, a.ref(), c.ref()))
 
     def matvec(self, which, x):
         nn = self.n if which == 0 else self.m

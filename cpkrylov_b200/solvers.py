@@ -154,14 +154,36 @@ def apply_opts_to_M(M, opts):
         M.ru_stateful = opts["ru_stateful"]
 
 
+def reg_solve_on(S, method, b, opts=None):
+    """The solve part of reg_cpkrylov (reg_cpkrylov.m:150-178) on an existing device system
+    ``S`` (KktSystem): rhs shift, Krylov loop, un-shift, in one launch.  Used for sequences
+    whose systems are refreshed in place (``S.update`` + ``S.M.refactor``)."""
+    name = _method_name(method)
+    n, m = S.n, S.m
+    apply_opts_to_M(S.M, opts)
+    tstarts = time.perf_counter()
+    b = _vec(b, n + m, "b")
+    sid, o = _fill_opts(name, opts, n, m)
+    cap = int(_lib.lib().cpk_hist_capacity(sid, ct.byref(o)))
+    hist = np.zeros((3, cap))
+    x = np.empty(n + m)
+    st = _lib.StatsStruct()
+    rc = _lib.lib().cpk_reg_solve(S.handle, sid, b.ctypes.data, ct.byref(o), x.ctypes.data, _lib.MEM_HOST,
+                                  ct.byref(st), hist.ctypes.data, cap)
+    stats, flag = _finish(name, st, hist, cap, rc, opts)
+    stats["stime"] = time.perf_counter() - tstarts
+    return x, stats, flag
+
+
 def reg_cpkrylov(method, b, A, B, Cm, G, opts=None, factors=None, ldl_method="auto", device=0,
-                 return_system=False):
+                 return_system=False, perm=None):
     """[x, stats, flag] = reg_cpkrylov(method, b, A, B, C, G, opts)   (reg_cpkrylov.m:1).
 
     ``method``: one of this module's solver functions (or its name).  Extra
     keyword arguments are not in the reference: ``factors=(L,d,e,perm)`` supplies
     the LDL' of [G B'; B -C] (e.g. MATLAB's ldl/MA57 output) instead of
-    factorizing here; ``device`` selects the GPU.
+    factorizing here, ``factors="device", perm=p`` factorizes on the GPU with the static
+    permutation p (symmetric quasi-definite K_P); ``device`` selects the GPU.
     """
     if method is None or b is None or A is None or B is None or Cm is None or G is None:
         raise ValueError("reg_cpkrylov: not enough inputs")                         # reg_cpkrylov.m:122-125
@@ -169,7 +191,7 @@ def reg_cpkrylov(method, b, A, B, Cm, G, opts=None, factors=None, ldl_method="au
     tstartp = time.perf_counter()
     B = sp.csc_matrix(B); Cm = sp.csc_matrix(Cm); G = sp.csc_matrix(G)
     n, m = A.shape[0], B.shape[0]
-    M = opLDL2(G, B, -Cm, factors=factors, ldl_method=ldl_method, device=device)    # :131
+    M = opLDL2(G, B, -Cm, factors=factors, ldl_method=ldl_method, device=device, perm=perm)    # :131
     S = KktSystem(A, Cm, M)
     ptime = time.perf_counter() - tstartp
     apply_opts_to_M(M, opts)

@@ -151,11 +151,34 @@ int  cpk_ldl2_matvec(cpk_handle M, const double *b, double *y, cpk_mem mem, cpk_
 int  cpk_ldl2_info(cpk_handle M, int64_t *nnz_L_off, int64_t *levels_fwd, int64_t *levels_bwd,
                    int64_t *n_2x2);
 
+/* ---- device-side factorization for sequences with a fixed pattern ----
+ * The reference re-assembles K_P and calls ldl for every system of an interior-point
+ * run (opLDL2.m:81-82).  For symmetric quasi-definite K_P = [A B'; B C] (A positive,
+ * C negative definite: every symmetric permutation has an LDL' factorization with a
+ * diagonal D) the library factorizes on the device with a STATIC permutation:
+ * perm[k] = original index of row k of the permuted matrix, chosen once for fill
+ * (e.g. the column permutation of a first host factorization).  One-CTA systems only
+ * (N <= ~11 000); A and C bring both triangles, as MATLAB stores them. */
+int  cpk_ldl2_create_sqd(cpk_handle *M, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
+                         const int64_t *perm, int device);
+/* next system of the sequence: new values, SAME sparsity patterns (entry order included).
+ * Symbolic work, level schedule and device layouts are reused; the numeric LDL' runs on
+ * the device and rewrites the operator in place. */
+int  cpk_ldl2_refactor(cpk_handle M, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C);
+/* the factor the device computed: strict lower triangle of L (CSC, pattern with fill) and
+ * diag(D).  Any output may be NULL; call once with colptr/rowind/Lval NULL to get nnz. */
+int  cpk_ldl2_get_factor(cpk_handle M, int64_t *nnz, int64_t *colptr, int64_t *rowind,
+                         double *Lval, double *d);
+
 /* ---- system = the (A, C, M) arguments of method(b1, A, C, M, opts) -------- */
 /* A n x n (may be nonsymmetric), C m x m symmetric, M from cpk_ldl2_create on
  * the same device.  B (m x n) is only used by cpk_reg_solve for the rhs shift
  * B'*y0 (reg_cpkrylov.m:157); it is taken from M. */
 int  cpk_system_create(cpk_handle *S, const cpk_csc *A, const cpk_csc *C, cpk_handle M);
+/* new values of A (= H) and C with the patterns the system was created with (the other
+ * half of a sequence step next to cpk_ldl2_refactor; reg_cpkrylov.m:1 takes A and C anew
+ * for every system) */
+int  cpk_system_update(cpk_handle S, const cpk_csc *A, const cpk_csc *C);
 /* y = A*x (which=0, n-vector) or y = C*x (which=1, m-vector): the sparse
  * mtimes call sites cpcg.m:151-152 etc. */
 int  cpk_system_matvec(cpk_handle S, int which, const double *x, double *y, cpk_mem mem,

@@ -994,3 +994,19 @@ def reg_cpkrylov(method, b, A, B, C, G, opts=None, factor=None, ru_stateful=Fals
     stats["napply"] = M.napply
     stats["nsolve"] = M.nsolve
     return x, stats, flag
+
+
+def ldl_static_perm(K, perm):
+    """Reference for the device-side factorization (cpk_ldl2_create_sqd): LDL' of
+    K[perm][:, perm] WITHOUT pivoting (natural order, diagonal pivots only) through
+    SuperLU's symmetric mode, as `ldl_superlu` does for its own ordering.  Returns
+    (L unit lower triangular CSC, d).  TEST INFRASTRUCTURE, like the rest of this file."""
+    import scipy.sparse.linalg as spla
+    perm = np.asarray(perm, dtype=np.int64)
+    Kp = sp.csc_matrix(K)[perm][:, perm].tocsc()
+    lu = spla.splu(Kp, permc_spec="NATURAL", diag_pivot_thresh=0.0, options={"SymmetricMode": True})
+    N = Kp.shape[0]
+    if not (np.array_equal(lu.perm_r, np.arange(N)) and np.array_equal(lu.perm_c, np.arange(N))):
+        raise RuntimeError("SuperLU left the natural order: the matrix is not strongly factorizable in this ordering")
+    d = lu.U.diagonal().copy()
+    return sp.csc_matrix(lu.L), d
