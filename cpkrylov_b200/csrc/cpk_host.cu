@@ -1040,9 +1040,11 @@ static int sqd_plan(const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const 
     std::vector<std::vector<std::pair<int, int>>> low(N);
     std::vector<int> diagsrc(N, -1);
     int64_t base = 0;
+    int64_t n_upper = 0, n_lower = 0;       // A and C must bring both triangles (as MATLAB stores symmetric matrices)
     auto add = [&](int64_t r, int64_t c, int64_t src, bool mirror_ok) {
         int pr = invp[r], pc = invp[c];
-        if (pr < pc) { if (!mirror_ok) return; std::swap(pr, pc); }       // A and C bring both triangles, B only one
+        if (!mirror_ok) { n_upper += pr < pc; n_lower += pr > pc; }
+        if (pr < pc) { if (!mirror_ok) return; std::swap(pr, pc); }       // the mirror entry of A / C carries this one; B has one copy
         if (pr == pc) { if (diagsrc[pc] < 0) diagsrc[pc] = (int)src; }
         else low[pc].emplace_back(pr, (int)src);
     };
@@ -1052,6 +1054,7 @@ static int sqd_plan(const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const 
     base += B->colptr[B->ncols];
     for (int64_t j = 0; j < C->ncols; ++j) for (int64_t k = C->colptr[j]; k < C->colptr[j + 1]; ++k) add(nA + C->rowind[k], nA + j, base + k, false);
     base += C->colptr[C->ncols];
+    if (n_upper != n_lower) return fail(CPK_ERR_ARG, "cpk_ldl2_create_sqd: A and C must be stored with both triangles (pattern is not symmetric)");
     P->nvals_in = base;
     P->nnzA = A->colptr[A->ncols]; P->nnzB = B->colptr[B->ncols]; P->nnzC = C->colptr[C->ncols];
     for (int k = 0; k < N; ++k) if (diagsrc[k] < 0) return fail(CPK_ERR_ARG, "K_P has a structurally zero diagonal entry (row %lld): not quasi-definite", (long long)perm[k]);

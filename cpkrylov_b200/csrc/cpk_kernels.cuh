@@ -507,15 +507,16 @@ __device__ __forceinline__ void compact_drain(Team &T, const DevLdl &M)
 
 // What a warp does in one step, held in registers.  It is fetched right after the
 // previous step's arithmetic, before the barrier, so that only gather -> arithmetic ->
-// store sit between two barriers.
-constexpr int kCwPre = 8;
+// store sit between two barriers.  Only the common shapes (<= 2 entries per lane) are
+// fetched ahead; wider items read their entries in place -- the interpreter is kept small
+// on purpose (instruction fetch and issue of ONE warp bound a level).
 struct CwTask {
     int kind, width, stride, z;
     bool barrier;
     const unsigned char *data;
     int t;                  // target index in sv, -1 = idle lane
-    int c[kCwPre];
-    double v[kCwPre];
+    int c0, c1;
+    double v0, v1;
 };
 
 __device__ __forceinline__ void cw_fetch(CwTask &I, const unsigned char *blk, const int4 tk, int lane)
@@ -524,36 +525,24 @@ __device__ __forceinline__ void cw_fetch(CwTask &I, const unsigned char *blk, co
     I.width = (tk.y >> 8) & 0xffff; I.stride = (tk.y >> 24) & 0xff;
     I.z = tk.z;
     I.data = blk + tk.x;
-    I.t = -1;
-    I.c[0] = -1; I.c[1] = -1; I.v[0] = 0.0; I.v[1] = 0.0;
+    I.t = -1; I.c0 = -1; I.c1 = -1; I.v0 = 0.0; I.v1 = 0.0;
     if (I.kind == CW_ROWS2) {
         if (lane < I.stride) {
             const int4 ri = *reinterpret_cast<const int4 *>(I.data + 32 * lane);
             const double2 rv = *reinterpret_cast<const double2 *>(I.data + 32 * lane + 16);
-            I.t = ri.x; I.c[0] = ri.y; I.c[1] = ri.z; I.v[0] = rv.x; I.v[1] = rv.y;
+            I.t = ri.x; I.c0 = ri.y; I.c1 = ri.z; I.v0 = rv.x; I.v1 = rv.y;
         }
-    } else if (I.kind == CW_ROWS || I.kind == CW_WARPROW) {
-        const int stride = I.stride, width = I.width;
-        const bool on = lane < stride;
-        const unsigned char *it = I.data;
-        if (I.kind == CW_ROWS) { if (on) I.t = reinterpret_cast<const int *>(it)[lane]; it += 4 * stride; }
-        else if (lane == 0) I.t = tk.z;
-        I.data = it;
-        const double *val = reinterpret_cast<const double *>(it);
-        const int *col = reinterpret_cast<const int *>(it + (size_t)8 * stride * width);
-        if (width <= 2) {
-            if (on) {
-                I.c[0] = col[lane]; I.v[0] = val[lane];
-                if (width == 2) { I.c[1] = col[stride + lane]; I.v[1] = val[stride + lane]; }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kCwPre; ++u) {
-                const bool have = on && u < width;
-                I.c[u] = have ? col[u * stride + lane] : -1;
-                I.v[u] = have ? val[u * stride + lane] : 0.0;
-            }
+    } else if (I.kind == CW_WARPROW) {
+        if (lane == 0) I.t = tk.z;
+        if (I.width <= 2) {
+            const double *val = reinterpret_cast<const double *>(I.data);
+            const int *col = reinterpret_cast<const int *>(I.data + (size_t)256 * I.width);
+            I.c0 = col[lane]; I.v0 = val[lane];
+            if (I.width == 2) { I.c1 = col[32 + lane]; I.v1 = val[32 + lane]; }
         }
+    } else if (I.kind == CW_ROWS) {
+        if (lane < I.stride) I.t = reinterpret_cast<const int *>(I.data)[lane];
+        I.data += 4 * I.stride;
     }
 }
 
@@ -563,23 +552,16 @@ __device__ __forceinline__ void cw_rows(const CwTask &I, double *sv, int lane)
     const double base = (I.t >= 0) ? sv[I.t] : 0.0;
     double sum = 0.0;
     if (I.width <= 2) {
-        const double x0 = (I.c[0] >= 0) ? sv[I.c[0]] : 0.0;
-        const double x1 = (I.c[1] >= 0) ? sv[I.c[1]] : 0.0;
-        if (I.c[0] >= 0) sum -= I.v[0] * x0;
-        if (I.c[1] >= 0) sum -= I.v[1] * x1;
-    } else {
-        double x[kCwPre];
-#pragma unroll
-        for (int u = 0; u < kCwPre; ++u) x[u] = (I.c[u] >= 0) ? sv[I.c[u]] : 0.0;
-#pragma unroll
-        for (int u = 0; u < kCwPre; ++u) if (I.c[u] >= 0) sum -= I.v[u] * x[u];
-        if (I.width > kCwPre && lane < I.stride) {
-            const double *val = reinterpret_cast<const double *>(I.data);
-            const int *col = reinterpret_cast<const int *>(I.data + (size_t)8 * I.stride * I.width);
-            for (int k = kCwPre; k < I.width; ++k) {
-                const int c = col[k * I.stride + lane];
-                if (c >= 0) sum -= val[k * I.stride + lane] * sv[c];
-            }
+        const double x0 = (I.c0 >= 0) ? sv[I.c0] : 0.0;
+        const double x1 = (I.c1 >= 0) ? sv[I.c1] : 0.0;
+        if (I.c0 >= 0) sum -= I.v0 * x0;
+        if (I.c1 >= 0) sum -= I.v1 * x1;
+    } else if (lane < I.stride) {
+        const double *val = reinterpret_cast<const double *>(I.data);
+        const int *col = reinterpret_cast<const int *>(I.data + (size_t)8 * I.stride * I.width);
+        for (int k = 0; k < I.width; ++k) {
+            const int c = col[k * I.stride + lane];
+            if (c >= 0) sum -= val[k * I.stride + lane] * sv[c];
         }
     }
     if (I.kind == CW_WARPROW) {
