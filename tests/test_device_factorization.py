@@ -145,3 +145,42 @@ def test_sequence_refactorized_in_place(meth):
             assert relerr(x, xo) <= 1e-7, (j, relerr(x, xo))
     finally:
         S.close()
+
+
+@pytest.mark.gpu
+def test_refactor_error_paths():
+    import cpkrylov_b200 as cp
+    from cpkrylov_b200.ldl import ldl_superlu
+    from cpkrylov_b200.operators import KktSystem
+    s = load_system("cvxqp2_s")
+    KP = kp_of(s)
+    # an operator built from host factors has no plan
+    Mh = cp.opLDL2(s["G"], s["A"], -s["C"], factors=ldl_superlu(KP))
+    with pytest.raises(_lib.CpkError):
+        Mh.refactor(s["G"], s["A"], -s["C"])
+    Mh.close()
+    perm = static_perm(KP)
+    M = cp.opLDL2(s["G"], s["A"], -s["C"], factors="device", perm=perm)
+    # another pattern is refused
+    A2 = s["A"].tolil(); A2[0, :] = 1.0
+    with pytest.raises(_lib.CpkError):
+        M.refactor(s["G"], A2.tocsc(), -s["C"])
+    # a singular pivot is reported, not propagated as NaN
+    with pytest.raises(_lib.CpkError) as ei:
+        Gz = s["G"].copy(); Gz.data[:] = 0.0           # same pattern, zero values: the first pivot vanishes
+        M.refactor(Gz, s["A"], -s["C"])
+    assert "pivot" in str(ei.value) or "pattern" in str(ei.value)
+    # after a refactorization the factor only lives in the compact-walk stream: a solver whose
+    # scratch leaves no room for it must fail loudly (cpdqgmres mem=140 needs ~170 KB of shared memory)
+    M.refactor(s["G"], s["A"], -s["C"])
+    S = KktSystem(s["Q"], s["C"], M)
+    try:
+        x, st, fl = cp.reg_solve_on(S, "cpgmres", s["rhs"], dict(EX_OPTS, restart=100))
+        xo, so, fo = orc.reg_cpkrylov("cpgmres", s["rhs"], s["Q"], s["A"], s["C"], s["G"], dict(EX_OPTS, restart=100),
+                                      factor=lambda K: ldl_superlu(KP))
+        assert fl["solved"] == fo["solved"] and abs(st["niters"] - so["niters"]) <= 2 and relerr(x, xo) <= 1e-7
+        with pytest.raises(_lib.CpkError) as ei:
+            cp.reg_solve_on(S, "cpdqgmres", s["rhs"], dict(EX_OPTS, mem=140))
+        assert "compact-walk stream" in str(ei.value)
+    finally:
+        S.close()

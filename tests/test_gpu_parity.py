@@ -329,7 +329,7 @@ def test_batch_of_ipm_systems_one_launch(cp):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("meth,extra", [("cpcg", {}), ("cpdqgmres", {"mem": 8})])
+@pytest.mark.parametrize("meth,extra", [("cpcg", {}), ("cpdqgmres", {"mem": 8}), ("cpgmres", {"restart": 6})])
 def test_batch_of_mid_size_systems_in_sub_teams(cp, meth, extra):
     """Systems too large for one CTA: the cooperative grid is cut into sub-teams, one system
     each, several systems per launch; a small system in the same call still goes to the one-CTA
