@@ -12,6 +12,9 @@
 //   y  = cpk_b200_mex('ldl2_matvec', h, b)                    M\b, opLDL2.m:193-195
 //   s  = cpk_b200_mex('system_create', A, C, h)               (A, C, M) of method(b1,A,C,M,opts)
 //   [x, niters, solved, status, hist] = cpk_b200_mex('reg_solve', s, solver_id, b, optsvec)
+//   h  = cpk_b200_mex('ldl2_create_sqd', G, B, C22, p)        device LDL' with the static permutation p (sequences)
+//        cpk_b200_mex('ldl2_refactor', h, G, B, C22)           next system: new values, same patterns
+//        cpk_b200_mex('system_update', s, A, C)                 ... and its A, C
 //        cpk_b200_mex('destroy', h)
 #include <cstring>
 #include <string>
@@ -70,6 +73,31 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         cpk_handle h = 0;
         fail_if(cpk_ldl2_create(&h, &m[0], &m[1], &m[2], &m[3], &m[4], perm.data(), 0));
         plhs[0] = mxCreateDoubleScalar((double)h);
+    } else if (cmd == "ldl2_create_sqd") {                        // G, B, C22, p  (p: 1-based permutation vector, e.g. from amd/symamd)
+        // symmetric quasi-definite K_P: numeric LDL' on the device with the static permutation p
+        // (replaces the ldl call of opLDL2.m:82 for the systems of a sequence)
+        if (nrhs != 5) mexErrMsgIdAndTxt("cpk_b200:arg", "Invalid number of arguments.");
+        std::vector<int64_t> jc[3], ir[3];
+        cpk_csc m[3];
+        for (int i = 0; i < 3; ++i) m[i] = as_csc(prhs[1 + i], jc[i], ir[i]);
+        const size_t N = mxGetNumberOfElements(prhs[4]);
+        const double *pv = mxGetDoubles(prhs[4]);
+        std::vector<int64_t> perm(N);
+        for (size_t k = 0; k < N; ++k) perm[k] = (int64_t)pv[k] - 1;
+        cpk_handle h = 0;
+        fail_if(cpk_ldl2_create_sqd(&h, &m[0], &m[1], &m[2], perm.data(), 0));
+        plhs[0] = mxCreateDoubleScalar((double)h);
+    } else if (cmd == "ldl2_refactor") {                          // h, G, B, C22: new values, same patterns
+        if (nrhs != 5) mexErrMsgIdAndTxt("cpk_b200:arg", "Invalid number of arguments.");
+        std::vector<int64_t> jc[3], ir[3];
+        cpk_csc m[3];
+        for (int i = 0; i < 3; ++i) m[i] = as_csc(prhs[2 + i], jc[i], ir[i]);
+        fail_if(cpk_ldl2_refactor(as_handle(prhs[1]), &m[0], &m[1], &m[2]));
+    } else if (cmd == "system_update") {                          // s, A, C: new values, same patterns
+        if (nrhs != 4) mexErrMsgIdAndTxt("cpk_b200:arg", "Invalid number of arguments.");
+        std::vector<int64_t> jc[2], ir[2];
+        cpk_csc a = as_csc(prhs[2], jc[0], ir[0]), c = as_csc(prhs[3], jc[1], ir[1]);
+        fail_if(cpk_system_update(as_handle(prhs[1]), &a, &c));
     } else if (cmd == "ldl2_set") {                               // h, name, value
         char name[32];
         mxGetString(prhs[2], name, sizeof name);
