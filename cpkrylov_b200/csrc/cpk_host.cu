@@ -45,554 +45,13 @@ static int fail(int code, const char *fmt, ...)
             return fail(CPK_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
     } while (0)
 
-// ===========================================================================
-// host sparse helpers
-// ===========================================================================
-struct HCsr {
-    int nrows = 0, ncols = 0;
-    std::vector<int64_t> ptr;
-    std::vector<int> col;
-    std::vector<double> val;
-    int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
-    int len(int r) const { return (int)(ptr[r + 1] - ptr[r]); }
-};
-
-static bool csc_ok(const cpk_csc *A)
-{
-    return A && A->nrows >= 0 && A->ncols >= 0 && A->colptr && (A->colptr[A->ncols] == 0 || (A->rowind && A->val));
-}
-
-// CSR of A (rows of A), from MATLAB CSC: a counting-sort transpose; column
-// indices inside a row come out ascending.
-static HCsr csr_from_csc(const cpk_csc &A)
-{
-    HCsr R;
-    R.nrows = (int)A.nrows; R.ncols = (int)A.ncols;
-    const int64_t nnz = A.colptr[A.ncols];
-    R.ptr.assign((size_t)R.nrows + 1, 0);
-    for (int64_t k = 0; k < nnz; ++k) R.ptr[A.rowind[k] + 1]++;
-    for (int i = 0; i < R.nrows; ++i) R.ptr[i + 1] += R.ptr[i];
-    R.col.resize(nnz); R.val.resize(nnz);
-    std::vector<int64_t> next(R.ptr.begin(), R.ptr.end() - 1);
-    for (int64_t j = 0; j < A.ncols; ++j)
-        for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; ++k) {
-            const int64_t p = next[A.rowind[k]]++;
-            R.col[p] = (int)j; R.val[p] = A.val[k];
-        }
-    return R;
-}
-// CSR of A' : the CSC arrays read as rows (sorted by index inside each row).
-static HCsr csr_of_transpose(const cpk_csc &A)
-{
-    HCsr R;
-    R.nrows = (int)A.ncols; R.ncols = (int)A.nrows;
-    const int64_t nnz = A.colptr[A.ncols];
-    R.ptr.assign(A.colptr, A.colptr + A.ncols + 1);
-    R.col.resize(nnz); R.val.resize(nnz);
-    for (int j = 0; j < R.nrows; ++j) {
-        const int64_t b = R.ptr[j], e = R.ptr[j + 1];
-        std::vector<std::pair<int, double>> tmp;
-        bool sorted = true;
-        for (int64_t k = b; k < e; ++k) {
-            if (k > b && A.rowind[k] < A.rowind[k - 1]) sorted = false;
-            R.col[k] = (int)A.rowind[k]; R.val[k] = A.val[k];
-        }
-        if (!sorted) {
-            tmp.reserve(e - b);
-            for (int64_t k = b; k < e; ++k) tmp.emplace_back(R.col[k], R.val[k]);
-            std::sort(tmp.begin(), tmp.end(), [](auto &x, auto &y) { return x.first < y.first; });
-            for (int64_t k = b; k < e; ++k) { R.col[k] = tmp[k - b].first; R.val[k] = tmp[k - b].second; }
-        }
-    }
-    return R;
-}
-
-// [A 0; 0 C] or general 2x2 block assembly by rows.  Blocks may be null (zero).
-static HCsr block2x2(const HCsr *A11, const HCsr *A12, const HCsr *A21, const HCsr *A22, int n1, int n2)
-{
-    HCsr R;
-    R.nrows = n1 + n2; R.ncols = n1 + n2;
-    R.ptr.assign((size_t)R.nrows + 1, 0);
-    auto rowlen = [](const HCsr *M, int r) { return M ? M->len(r) : 0; };
-    for (int i = 0; i < n1; ++i) R.ptr[i + 1] = R.ptr[i] + rowlen(A11, i) + rowlen(A12, i);
-    for (int i = 0; i < n2; ++i) R.ptr[n1 + i + 1] = R.ptr[n1 + i] + rowlen(A21, i) + rowlen(A22, i);
-    R.col.resize(R.ptr.back()); R.val.resize(R.ptr.back());
-    auto put = [&](const HCsr *M, int r, int off, int64_t &p) {
-        if (!M) return;
-        for (int64_t k = M->ptr[r]; k < M->ptr[r + 1]; ++k) { R.col[p] = M->col[k] + off; R.val[p] = M->val[k]; ++p; }
-    };
-    for (int i = 0; i < n1; ++i) { int64_t p = R.ptr[i]; put(A11, i, 0, p); put(A12, i, n1, p); }
-    for (int i = 0; i < n2; ++i) { int64_t p = R.ptr[n1 + i]; put(A21, i, 0, p); put(A22, i, n1, p); }
-    return R;
-}
-
-// ---------------------------------------------------------------------------
-// SELL-32-sigma builder.  Rows are stably sorted by length inside windows of
-// `sigma` rows (keeps x-locality, removes padding), cut into slices of 32.
-// Rows much longer than the mean go to the CSR "long" list (warp per row).
-// ---------------------------------------------------------------------------
-struct HSell {
-    int nrows = 0, ncols = 0, nslices = 0;
-    std::vector<int> sptr, col, rowmap;
-    std::vector<double> val;
-    std::vector<int> lrow, lptr, lcol;
-    std::vector<double> lval;
-    int64_t nnz = 0;
-};
-
-static int sell_sigma()
-{
-    static int s = [] { const char *e = getenv("CPK_SELL_SIGMA"); int v = e ? atoi(e) : 4096; return std::max(32, v / 32 * 32); }();
-    return s;
-}
-
-// Appends the rows [r0, r1) of A (column offset coff, row offset roff) as new slices.
-static void sell_append(HSell &S, const HCsr &A, int r0, int r1, int coff, int roff)
-{
-    const int64_t nnz = A.ptr[r1] - A.ptr[r0];
-    const double mean = (r1 > r0) ? (double)nnz / (r1 - r0) : 0.0;
-    const int long_thr = (int)std::max(128.0, 8.0 * mean);
-    std::vector<int> rows;
-    rows.reserve(r1 - r0);
-    for (int r = r0; r < r1; ++r) {
-        if (A.len(r) > long_thr) {
-            if (S.lptr.empty()) S.lptr.push_back(0);
-            S.lrow.push_back(r + roff);
-            for (int64_t k = A.ptr[r]; k < A.ptr[r + 1]; ++k) { S.lcol.push_back(A.col[k] + coff); S.lval.push_back(A.val[k]); }
-            S.lptr.push_back((int)S.lcol.size());
-        } else rows.push_back(r);
-    }
-    const int sigma = sell_sigma();
-    if (S.sptr.empty()) S.sptr.push_back(0);
-    for (size_t w0 = 0; w0 < rows.size(); w0 += sigma) {
-        const size_t w1 = std::min(rows.size(), w0 + (size_t)sigma);
-        std::stable_sort(rows.begin() + w0, rows.begin() + w1, [&](int a, int b) { return A.len(a) > A.len(b); });
-        for (size_t s0 = w0; s0 < w1; s0 += 32) {
-            const size_t s1 = std::min(w1, s0 + 32);
-            int width = 0;
-            for (size_t t = s0; t < s1; ++t) width = std::max(width, A.len(rows[t]));
-            const size_t base = S.col.size();
-            S.col.resize(base + (size_t)width * 32, 0);
-            S.val.resize(base + (size_t)width * 32, 0.0);
-            for (int lane = 0; lane < 32; ++lane) {
-                const size_t t = s0 + lane;
-                if (t < s1) {
-                    const int r = rows[t];
-                    S.rowmap.push_back(r + roff);
-                    const int len = A.len(r);
-                    int lastc = 0;
-                    for (int j = 0; j < width; ++j) {
-                        if (j < len) {
-                            lastc = A.col[A.ptr[r] + j] + coff;
-                            S.col[base + (size_t)j * 32 + lane] = lastc;
-                            S.val[base + (size_t)j * 32 + lane] = A.val[A.ptr[r] + j];
-                        } else S.col[base + (size_t)j * 32 + lane] = lastc;
-                    }
-                } else S.rowmap.push_back(-1);
-            }
-            S.sptr.push_back((int)S.col.size());
-            S.nslices++;
-        }
-    }
-    S.nnz += nnz;
-}
-
-static HSell build_sell(const HCsr &A)
-{
-    HSell S;
-    S.nrows = A.nrows; S.ncols = A.ncols;
-    sell_append(S, A, 0, A.nrows, 0, 0);
-    if (S.sptr.empty()) S.sptr.push_back(0);
-    if (S.lptr.empty()) S.lptr.push_back(0);
-    return S;
-}
-
-// ---------------------------------------------------------------------------
-// LDL' sweep builder.  Produces the unified item list of DevSweep: forward items
-// (level order), then backward items (level order), with the rows that need no
-// work compiled away (see cpk_device.cuh) and the segment table that tells the
-// kernel how to deal items to warps (blocks of consecutive items for bulk
-// levels, one item per warp for chains).
-// ---------------------------------------------------------------------------
-struct HSweep {
-    int nitems = 0, nfwd = 0;
-    std::vector<int> seg, levptr, sptr, col, rid, pidx, flags, partner;
-    std::vector<double> val, d, e, dp;
-    int64_t n_trivial = 0, n_fused = 0, tail_f = 0, tail_b = 0, n_warprow = 0, max_len = 0;
-    int lev_f_eff = 0, lev_b_eff = 0;
-};
-
-struct SweepRow { int row; int level; int len; };
-constexpr int kLongRow = 8;         // rows with more entries are walked by a whole warp
-typedef std::vector<std::pair<int, double>> EncRow;     // (column code, value), in accumulation order
-
-// Appends the rows (already filtered) of one direction.  `entries(r)` returns the
-// encoded dependency list of LDL row r.
-// Items of a level are created sorted by cost (long rows first).  Deal them
-// round-robin to the `nw` warps that will walk the level and store every
-// warp's hand contiguously: each warp still streams a contiguous range, and
-// every range holds the same mix of expensive and cheap items.
-static void deal_level(HSweep &W, int first, int n, int nw)
-{
-    if (n <= 1 || nw <= 1) return;
-    std::vector<int> order;             // new position -> old item (relative)
-    order.reserve(n);
-    // warp w gets [n*w/nw, n*(w+1)/nw): fill these ranges by dealing
-    std::vector<std::vector<int>> hand(std::min(nw, n));
-    const int nh = (int)hand.size();
-    // ranges have sizes that differ by at most one; deal so that range sizes match
-    std::vector<int> cap(nh);
-    for (int w = 0; w < nh; ++w) cap[w] = (int)((long long)n * (w + 1) / nh) - (int)((long long)n * w / nh);
-    int w = 0;
-    for (int i = 0; i < n; ++i) {
-        int tries = 0;
-        while ((int)hand[w].size() >= cap[w] && tries < nh) { w = (w + 1) % nh; ++tries; }
-        hand[w].push_back(i);
-        w = (w + 1) % nh;
-    }
-    for (auto &h : hand) for (int i : h) order.push_back(i);
-    // rebuild the item arrays of this level in the new order
-    const int s0 = W.sptr[first];
-    std::vector<int> col, sptr(1, s0), rid, pidx, flags, partner;
-    std::vector<double> val, d, e, dp;
-    for (int k = 0; k < n; ++k) {
-        const int it = first + order[k];
-        const int b = W.sptr[it], en = W.sptr[it + 1];
-        col.insert(col.end(), W.col.begin() + b, W.col.begin() + en);
-        val.insert(val.end(), W.val.begin() + b, W.val.begin() + en);
-        sptr.push_back(s0 + (int)col.size());
-        for (int l = 0; l < 32; ++l) {
-            const size_t sl = (size_t)it * 32 + l;
-            rid.push_back(W.rid[sl]); pidx.push_back(W.pidx[sl]); flags.push_back(W.flags[sl]); partner.push_back(W.partner[sl]);
-            d.push_back(W.d[sl]); e.push_back(W.e[sl]); dp.push_back(W.dp[sl]);
-        }
-    }
-    std::copy(col.begin(), col.end(), W.col.begin() + s0);
-    std::copy(val.begin(), val.end(), W.val.begin() + s0);
-    for (int k = 0; k <= n; ++k) W.sptr[first + k] = sptr[k];
-    const size_t base = (size_t)first * 32;
-    std::copy(rid.begin(), rid.end(), W.rid.begin() + base);
-    std::copy(pidx.begin(), pidx.end(), W.pidx.begin() + base);
-    std::copy(flags.begin(), flags.end(), W.flags.begin() + base);
-    std::copy(partner.begin(), partner.end(), W.partner.begin() + base);
-    std::copy(d.begin(), d.end(), W.d.begin() + base);
-    std::copy(e.begin(), e.end(), W.e.begin() + base);
-    std::copy(dp.begin(), dp.end(), W.dp.begin() + base);
-}
-
-template <class Entries, class Flags>
-static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vector<int64_t> &perm,
-                         const std::vector<double> &dd, const std::vector<double> &ee, const std::vector<int> &partner,
-                         int grid_warps, Entries entries, Flags flags_of)
-{
-    // the team shape that will walk this system: whole grid for large N, one CTA otherwise
-    const int deal_warps = (int)perm.size() > 24576 ? grid_warps : kWarpsPerCta;
-    // inside a level any order is valid: group rows of equal (short) length and
-    // order them by their index in the user vector, so that the P' gather and the
-    // P scatter of consecutive lanes touch consecutive addresses
-    for (auto &rw : rows) W.max_len = std::max<int64_t>(W.max_len, rw.len);
-    std::stable_sort(rows.begin(), rows.end(), [&](const SweepRow &a, const SweepRow &b) {
-        if (a.level != b.level) return a.level < b.level;
-        const int la = std::min(a.len, kLongRow + 1), lb = std::min(b.len, kLongRow + 1);
-        if (la != lb) return la > lb;
-        return perm[a.row] < perm[b.row];
-    });
-    if (W.sptr.empty()) W.sptr.push_back(0);
-    // items per level
-    std::vector<std::pair<int, int>> level_items;       // (first item, count) per level, in order
-    size_t i0 = 0;
-    while (i0 < rows.size()) {
-        const int lev = rows[i0].level;
-        const int first_item = W.nitems;
-        while (i0 < rows.size() && rows[i0].level == lev) {
-            if (rows[i0].len > kLongRow) {
-                // one long row = one item, entries spread over the 32 lanes
-                const int r = rows[i0].row;
-                const EncRow er = entries(r);
-                const size_t width = (er.size() + 31) / 32;
-                const size_t base = W.col.size();
-                W.col.resize(base + width * 32, -1);
-                W.val.resize(base + width * 32, 0.0);
-                for (size_t jx = 0; jx < er.size(); ++jx) { W.col[base + jx] = er[jx].first; W.val[base + jx] = er[jx].second; }
-                for (int lane = 0; lane < 32; ++lane) {
-                    if (lane == 0) {
-                        W.rid.push_back(r); W.pidx.push_back((int)perm[r]); W.flags.push_back(flags_of(r) | F_WARPROW); W.d.push_back(dd[r]);
-                        if (partner[r] >= 0) { W.partner.push_back(partner[r]); W.e.push_back(ee[std::min(r, partner[r])]); W.dp.push_back(dd[partner[r]]); }
-                        else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
-                    } else {
-                        W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
-                        W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
-                    }
-                }
-                W.sptr.push_back((int)W.col.size());
-                W.nitems++; W.n_warprow++;
-                ++i0;
-                continue;
-            }
-            size_t i1 = i0;
-            while (i1 < rows.size() && i1 - i0 < 32 && rows[i1].level == lev && rows[i1].len <= kLongRow) ++i1;
-            int width = 0;
-            for (size_t t = i0; t < i1; ++t) width = std::max(width, rows[t].len);
-            const size_t base = W.col.size();
-            W.col.resize(base + (size_t)width * 32, -1);
-            W.val.resize(base + (size_t)width * 32, 0.0);
-            for (int lane = 0; lane < 32; ++lane) {
-                const size_t t = i0 + lane;
-                if (t < i1) {
-                    const int r = rows[t].row;
-                    W.rid.push_back(r);
-                    W.pidx.push_back((int)perm[r]);
-                    W.flags.push_back(flags_of(r));
-                    W.d.push_back(dd[r]);
-                    if (partner[r] >= 0) {
-                        W.partner.push_back(partner[r]);
-                        W.e.push_back(ee[std::min(r, partner[r])]);
-                        W.dp.push_back(dd[partner[r]]);
-                    } else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
-                    const EncRow er = entries(r);
-                    for (size_t jx = 0; jx < er.size(); ++jx) {
-                        W.col[base + jx * 32 + lane] = er[jx].first;
-                        W.val[base + jx * 32 + lane] = er[jx].second;
-                    }
-                } else {
-                    W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
-                    W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
-                }
-            }
-            W.sptr.push_back((int)W.col.size());
-            W.nitems++;
-            i0 = i1;
-        }
-        level_items.emplace_back(first_item, W.nitems - first_item);
-        W.levptr.push_back(first_item);
-        deal_level(W, first_item, W.nitems - first_item, deal_warps);
-    }
-    // segments: a level with at least 2 items per warp is "bulk" (blocks of
-    // consecutive items per warp); runs of smaller levels
-    // are merged into one chain segment dealt round-robin.
-    int chain_first = -1, chain_end = -1;
-    auto flush_chain = [&]() {
-        if (chain_first >= 0) { W.seg.push_back(chain_first); W.seg.push_back(chain_end); W.seg.push_back(1); }
-        chain_first = -1;
-    };
-    static const double bulk_min = [] { const char *e = getenv("CPK_LDL_BULK_MIN"); return e ? atof(e) : 2.0; }();
-    static const int blk_max = [] { const char *e = getenv("CPK_LDL_BLK"); return e ? atoi(e) : 8; }();
-    for (auto &li : level_items) {
-        if (li.second >= bulk_min * grid_warps) {
-            flush_chain();
-            const int blk = std::max(1, std::min(blk_max, li.second / grid_warps));
-            W.seg.push_back(li.first); W.seg.push_back(li.first + li.second); W.seg.push_back(blk);
-        } else {
-            if (chain_first < 0) chain_first = li.first;
-            chain_end = li.first + li.second;
-        }
-    }
-    flush_chain();
-}
+#include "cpk_host_sparse.hpp"
+#include "cpk_host_sweep.hpp"
 
 // ===========================================================================
 // device objects
 // ===========================================================================
-// ---------------------------------------------------------------------------
-// Stream builder of the compact (one-CTA) walk: see DevCompact in cpk_device.cuh.
-// A "step" is a set of items that may run concurrently and ends with a CTA
-// barrier; a dependency level is one step (plus one step per extra part of rows
-// too long for a single item).  Runs of one-item steps become CW_SEQ groups.
-// ---------------------------------------------------------------------------
-struct CwItemH {
-    int kind;                               // CW_ROWS / CW_WARPROW / CW_DCHUNK
-    int width, stride;                      // D chunk: count in `width`, has2x2 in `stride`
-    int z;                                  // warp-row: target; D chunk: first row
-    std::vector<unsigned char> data;        // multiple of 16 bytes
-};
-
-struct CwStream {
-    std::vector<unsigned char> bytes;       // finished blocks
-    int nblk = 0;
-    // block under construction
-    std::vector<int> table;                 // 4 ints per slot, kWarpsPerCta slots per step
-    std::vector<unsigned char> blob;
-    long long n_levels = 0, n_steps = 0, n_items = 0;
-    int rot = 0;                            // first warp of the next step (rotates, so that the warp
-                                            // busy in one step is rarely the one busy in the next)
-    size_t used(size_t more_steps, size_t more_bytes) const {
-        return 16 + 4 * table.size() + 16 * kWarpsPerCta * more_steps + blob.size() + more_bytes;
-    }
-    void flush() {
-        if (table.empty()) return;
-        const size_t nsteps = table.size() / (4 * kWarpsPerCta);
-        const size_t area = 16 + 4 * table.size();
-        std::vector<unsigned char> blk(kCwBlock, 0);
-        int *h = reinterpret_cast<int *>(blk.data());
-        h[0] = (int)nsteps;
-        int *dst = h + 4;
-        for (size_t i = 0; i < table.size(); i += 4) {
-            dst[i] = table[i] + ((table[i + 1] & 15) ? (int)area : 0);
-            dst[i + 1] = table[i + 1]; dst[i + 2] = table[i + 2]; dst[i + 3] = table[i + 3];
-        }
-        if (!blob.empty()) memcpy(blk.data() + area, blob.data(), blob.size());
-        bytes.insert(bytes.end(), blk.begin(), blk.end());
-        ++nblk;
-        table.clear(); blob.clear();
-    }
-    // appends one step (a row of kWarpsPerCta empty slots) and returns its first slot
-    size_t new_step() { table.resize(table.size() + 4 * kWarpsPerCta, 0); ++n_steps; return table.size() - 4 * kWarpsPerCta; }
-    void set_slot(size_t step0, int w, int off, const CwItemH &it) {
-        int *sl = &table[step0 + 4 * w];
-        sl[0] = off; sl[1] = it.kind | (it.width << 8) | (it.stride << 24); sl[2] = it.z;
-    }
-    int put_data(const CwItemH &it) {
-        const int off = (int)blob.size();
-        blob.insert(blob.end(), it.data.begin(), it.data.end());
-        ++n_items;
-        return off;
-    }
-    void barrier_after(size_t step0) { for (int w = 0; w < kWarpsPerCta; ++w) table[step0 + 4 * w + 1] |= CW_BARRIER; }
-    // One dependency level (or the D pass): its items run concurrently, a CTA barrier
-    // closes it.  More than kWarpsPerCta items take several steps, only the last has the barrier.
-    void level(const std::vector<CwItemH> &items) {
-        if (items.empty()) return;
-        ++n_levels;
-        if (items[0].kind == CW_DCHUNK) {
-            size_t st = 0;
-            for (auto &it : items) {        // a chunk is shared by all warps: warp w takes rows 32w .. 32w+31
-                if (used(1, it.data.size()) > (size_t)kCwBlock) flush();
-                st = new_step();
-                const int off = put_data(it);
-                for (int w = 0; w < kWarpsPerCta; ++w) if (32 * w < it.width) set_slot(st, w, off, it);
-            }
-            barrier_after(st);
-            return;
-        }
-        size_t i = 0, st = 0;
-        while (i < items.size()) {
-            if (used(1, items[i].data.size()) > (size_t)kCwBlock) flush();      // the level continues in the next block
-            st = new_step();
-            for (int q = 0; q < kWarpsPerCta && i < items.size(); ++q) {
-                if (used(0, items[i].data.size()) > (size_t)kCwBlock) break;
-                set_slot(st, (rot + q) % kWarpsPerCta, put_data(items[i]), items[i]);
-                ++i;
-            }
-            rot = (rot + 5) % kWarpsPerCta;
-        }
-        barrier_after(st);
-    }
-};
-
-static void cw_put(std::vector<unsigned char> &b, const void *src, size_t n)
-{
-    const unsigned char *s = static_cast<const unsigned char *>(src);
-    if (n) b.insert(b.end(), s, s + n);
-}
-
-// items of one sweep direction.  R.row(i) = dependency list of LDL row i as (row id, value);
-// `toff`/`coff`: offsets of the target and of the dependencies in the shared vector sv[2N].
-static void cw_sweep(CwStream &S, int N, const HCsr &R, const std::vector<int> &lev, int nlev, int toff, int coff)
-{
-    constexpr int kMaxWidth = 16;           // entries per lane in one item
-    std::vector<std::vector<int>> byLevel(nlev);
-    for (int i = 0; i < N; ++i) if (R.len(i) > 0) byLevel[lev[i]].push_back(i);
-    typedef std::vector<CwItemH> Items;
-    auto emit = [&](Items &&items) { S.level(items); };
-    for (int l = 0; l < nlev; ++l) {
-        std::vector<int> &rows = byLevel[l];
-        if (rows.empty()) continue;
-        std::stable_sort(rows.begin(), rows.end(), [&](int a, int b) { return R.len(a) < R.len(b); });
-        Items first;
-        std::vector<Items> later;           // later[j-1] = parts j of the long rows
-        size_t k = 0;
-        // short rows: up to 32 per item, one lane each
-        while (k < rows.size() && R.len(rows[k]) <= kLongRow) {
-            size_t k1 = k;
-            int width = 0;
-            while (k1 < rows.size() && k1 - k < 32 && R.len(rows[k1]) <= kLongRow) { width = std::max(width, R.len(rows[k1])); ++k1; }
-            const int stride = ((int)(k1 - k) + 3) & ~3;        // lanes stored (idle lanes of a thin item are not)
-            CwItemH it{width <= 2 ? CW_ROWS2 : CW_ROWS, width, stride, 0, {}};
-            if (width <= 2) {
-                // one 32-byte record per lane: {target, col0, col1, 0, val0, val1}
-                for (int q = 0; q < stride; ++q) {
-                    int rec_i[4] = {-1, -1, -1, 0};
-                    double rec_v[2] = {0.0, 0.0};
-                    if (k + q < k1) {
-                        const int r = rows[k + q];
-                        rec_i[0] = toff + r;
-                        for (int j = 0; j < R.len(r); ++j) { rec_i[1 + j] = coff + R.col[R.ptr[r] + j]; rec_v[j] = R.val[R.ptr[r] + j]; }
-                    }
-                    cw_put(it.data, rec_i, 16);
-                    cw_put(it.data, rec_v, 16);
-                }
-            } else {
-                int tgt[32];
-                for (int q = 0; q < 32; ++q) tgt[q] = (k + q < k1) ? toff + rows[k + q] : -1;
-                cw_put(it.data, tgt, (size_t)4 * stride);
-                std::vector<double> val((size_t)width * stride, 0.0);
-                std::vector<int> col((size_t)width * stride, -1);
-                for (size_t q = k; q < k1; ++q) {
-                    const int r = rows[q];
-                    for (int j = 0; j < R.len(r); ++j) {
-                        val[(size_t)j * stride + (q - k)] = R.val[R.ptr[r] + j];
-                        col[(size_t)j * stride + (q - k)] = coff + R.col[R.ptr[r] + j];
-                    }
-                }
-                cw_put(it.data, val.data(), val.size() * 8);
-                cw_put(it.data, col.data(), col.size() * 4);
-            }
-            first.push_back(std::move(it));
-            k = k1;
-        }
-        // long rows: the 32 lanes share the row, <= 32*kMaxWidth entries per part
-        for (; k < rows.size(); ++k) {
-            const int r = rows[k], len = R.len(r);
-            int part = 0;
-            for (int e0 = 0; e0 < len; e0 += 32 * kMaxWidth, ++part) {
-                const int cnt = std::min(len - e0, 32 * kMaxWidth);
-                const int width = (cnt + 31) / 32;
-                CwItemH it{CW_WARPROW, width, 32, toff + r, {}};
-                std::vector<double> val((size_t)width * 32, 0.0);
-                std::vector<int> col((size_t)width * 32, -1);
-                for (int j = 0; j < cnt; ++j) { val[j] = R.val[R.ptr[r] + e0 + j]; col[j] = coff + R.col[R.ptr[r] + e0 + j]; }
-                cw_put(it.data, val.data(), val.size() * 8);
-                cw_put(it.data, col.data(), col.size() * 4);
-                if (part == 0) first.push_back(std::move(it));
-                else {
-                    if ((int)later.size() < part) later.resize(part);
-                    later[part - 1].push_back(std::move(it));
-                }
-            }
-        }
-        emit(std::move(first));
-        for (auto &st : later) emit(std::move(st));
-    }
-}
-
-static void cw_dpass(CwStream &S, int N, const std::vector<double> &d, const std::vector<double> &e, const std::vector<int> &partner)
-{
-    std::vector<CwItemH> items;
-    for (int i0 = 0; i0 < N;) {
-        bool has2 = false;
-        int cnt = std::min(512, N - i0);
-        for (int r = 0; r < cnt; ++r) has2 = has2 || partner[i0 + r] >= 0;
-        if (has2) cnt = std::min(cnt, 256);
-        CwItemH it{CW_DCHUNK, cnt, has2 ? 1 : 0, i0, {}};
-        cw_put(it.data, &d[i0], (size_t)cnt * 8);
-        if (has2) {
-            std::vector<double> ee(cnt, 0.0), dp(cnt, 1.0);
-            std::vector<int> pr(cnt, -1);
-            for (int r = 0; r < cnt; ++r) {
-                const int i = i0 + r, q = partner[i];
-                if (q < 0) continue;
-                pr[r] = q; dp[r] = d[q]; ee[r] = e[std::min(i, q)];
-            }
-            cw_put(it.data, ee.data(), (size_t)cnt * 8);
-            cw_put(it.data, dp.data(), (size_t)cnt * 8);
-            cw_put(it.data, pr.data(), (size_t)cnt * 4);
-        }
-        while (it.data.size() % 16) it.data.push_back(0);
-        items.push_back(std::move(it));
-        i0 += cnt;
-    }
-    S.level(items);
-}
+#include "cpk_host_compact.hpp"
 
 // Device memory of one object.  Arrays come from the device's stream-ordered pool
 // (cudaMallocAsync on the legacy stream, release threshold = keep everything): a small system
@@ -993,153 +452,8 @@ extern "C" int cpk_debug_barrier_cycles(int device, int iters, double *sync_cycl
     return CPK_OK;
 }
 
-// ===========================================================================
-// Numeric LDL' on the device for symmetric quasi-definite K_P with a STATIC
-// permutation (a sequence of interior-point systems keeps
-// its pattern, opLDL2.m:81-82 re-assembles and re-factors each of them from scratch).
-// Quasi-definite matrices are strongly factorizable: every symmetric permutation has
-// an LDL' factorization with a diagonal D, so the permutation is chosen once for
-// fill and the numeric work is a fixed dependency graph:
-//     d_k  = a_kk - sum_j L_kj^2 d_j
-//     L_ik = (a_ik - sum_j L_ij d_j L_kj) / d_k          (j < k, both factors nonzero)
-// The host compiles that graph once per pattern ("plan"): every entry of L and D is a
-// node with its list of triple products, nodes are sorted into dependency levels, and
-// one CTA evaluates level after level.  The plan also records where every value sits
-// in the compact-walk stream, so a refactorization rewrites the operator in place.
-// ===========================================================================
-struct SqdPlan {
-    int N = 0;
-    int64_t nnzL = 0, ne = 0, nops = 0, nvals_in = 0;
-    int nlev = 0;
-    std::vector<int64_t> colptr, rowind;    // strict lower triangle of L, CSC (symbolic pattern incl. fill)
-    int64_t nnzA = 0, nnzB = 0, nnzC = 0;   // lengths of the value arrays a refactorization must bring
-    // device copies
-    DevArena ar;
-    double *d_fval = nullptr, *d_vals_in = nullptr;
-    const int *d_asrc = nullptr, *d_dk = nullptr, *d_exec = nullptr, *d_levptr = nullptr, *d_opptr = nullptr, *d_ops = nullptr;
-    const int *d_spos = nullptr, *d_ssrc = nullptr;
-    int64_t ns = 0;
-};
+#include "cpk_host_sqd.hpp"
 Ldl2::~Ldl2() {}
-
-struct SqdHost {
-    std::vector<int> asrc, dk, exec, levptr, opptr, ops;
-};
-
-// symbolic analysis + plan.  K_P = [A B'; B C] (blocks as handed to cpk_ldl2_create), perm[k] =
-// original index of row k of the permuted matrix.
-static int sqd_plan(const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int N, int nA,
-                    SqdPlan *P, SqdHost *H)
-{
-    std::vector<int> invp(N, -1);
-    for (int k = 0; k < N; ++k) {
-        if (perm[k] < 0 || perm[k] >= N || invp[perm[k]] >= 0) return fail(CPK_ERR_ARG, "perm is not a permutation of 0..N-1");
-        invp[perm[k]] = k;
-    }
-    // lower triangle of P' K_P P by columns: (row, index into the concatenated values [A | B | C])
-    std::vector<std::vector<std::pair<int, int>>> low(N);
-    std::vector<int> diagsrc(N, -1);
-    int64_t base = 0;
-    int64_t n_upper = 0, n_lower = 0;       // A and C must bring both triangles (as MATLAB stores symmetric matrices)
-    auto add = [&](int64_t r, int64_t c, int64_t src, bool mirror_ok) {
-        int pr = invp[r], pc = invp[c];
-        if (!mirror_ok) { n_upper += pr < pc; n_lower += pr > pc; }
-        if (pr < pc) { if (!mirror_ok) return; std::swap(pr, pc); }       // the mirror entry of A / C carries this one; B has one copy
-        if (pr == pc) { if (diagsrc[pc] < 0) diagsrc[pc] = (int)src; }
-        else low[pc].emplace_back(pr, (int)src);
-    };
-    for (int64_t j = 0; j < A->ncols; ++j) for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; ++k) add(A->rowind[k], j, base + k, false);
-    base += A->colptr[A->ncols];
-    for (int64_t j = 0; j < B->ncols; ++j) for (int64_t k = B->colptr[j]; k < B->colptr[j + 1]; ++k) add(nA + B->rowind[k], j, base + k, true);
-    base += B->colptr[B->ncols];
-    for (int64_t j = 0; j < C->ncols; ++j) for (int64_t k = C->colptr[j]; k < C->colptr[j + 1]; ++k) add(nA + C->rowind[k], nA + j, base + k, false);
-    base += C->colptr[C->ncols];
-    if (n_upper != n_lower) return fail(CPK_ERR_ARG, "cpk_ldl2_create_sqd: A and C must be stored with both triangles (pattern is not symmetric)");
-    P->nvals_in = base;
-    P->nnzA = A->colptr[A->ncols]; P->nnzB = B->colptr[B->ncols]; P->nnzC = C->colptr[C->ncols];
-    for (int k = 0; k < N; ++k) if (diagsrc[k] < 0) return fail(CPK_ERR_ARG, "K_P has a structurally zero diagonal entry (row %lld): not quasi-definite", (long long)perm[k]);
-    // column structures with fill (elimination tree: parent = first off-diagonal row)
-    std::vector<std::vector<int>> st(N), children(N);
-    std::vector<int> mark(N, -1);
-    for (int k = 0; k < N; ++k) {
-        std::vector<int> &sk = st[k];
-        for (auto &e : low[k]) if (mark[e.first] != k) { mark[e.first] = k; sk.push_back(e.first); }
-        for (int c : children[k]) for (int i : st[c]) if (i != k && mark[i] != k) { mark[i] = k; sk.push_back(i); }
-        std::sort(sk.begin(), sk.end());
-        if (!sk.empty()) children[sk[0]].push_back(k);
-    }
-    P->N = N;
-    P->colptr.assign(N + 1, 0);
-    for (int k = 0; k < N; ++k) P->colptr[k + 1] = P->colptr[k] + (int64_t)st[k].size();
-    P->nnzL = P->colptr[N];
-    P->ne = P->nnzL + N;
-    if (P->ne >= INT32_MAX / 2) return fail(CPK_ERR_UNSUPPORTED, "factor too large for the device factorization plan");
-    P->rowind.resize(P->nnzL);
-    for (int k = 0; k < N; ++k) std::copy(st[k].begin(), st[k].end(), P->rowind.begin() + P->colptr[k]);
-    const int ne = (int)P->ne, nnzL = (int)P->nnzL;
-    auto id_of = [&](int i, int k) -> int {         // entry (i,k), i > k
-        const auto &sk = st[k];
-        return (int)(P->colptr[k] + (std::lower_bound(sk.begin(), sk.end(), i) - sk.begin()));
-    };
-    H->asrc.assign(ne, -1);
-    H->dk.assign(ne, -1);
-    for (int k = 0; k < N; ++k) {
-        H->asrc[nnzL + k] = diagsrc[k];
-        for (auto &e : low[k]) { const int id = id_of(e.first, k); if (H->asrc[id] < 0) H->asrc[id] = e.second; }
-        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) H->dk[q] = nnzL + k;
-    }
-    // rows of L: (column j, entry id) with j ascending
-    std::vector<std::vector<std::pair<int, int>>> rowc(N);
-    for (int j = 0; j < N; ++j) for (int64_t q = P->colptr[j]; q < P->colptr[j + 1]; ++q) rowc[P->rowind[q]].emplace_back(j, (int)q);
-    // triple products of every node, j ascending
-    std::vector<int> lev(ne, 0), pos(N, -1);
-    std::vector<std::vector<int>> opl(ne);
-    int64_t nops = 0;
-    for (int k = 0; k < N; ++k) {
-        pos[k] = nnzL + k;
-        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) pos[P->rowind[q]] = (int)q;
-        for (auto &kj : rowc[k]) {
-            const int j = kj.first, id_kj = kj.second;
-            const auto &sj = st[j];
-            for (size_t t = std::lower_bound(sj.begin(), sj.end(), k) - sj.begin(); t < sj.size(); ++t) {
-                const int i = sj[t];
-                const int id_ij = (int)(P->colptr[j] + t);
-                if (i != k && (pos[i] < P->colptr[k] || pos[i] >= P->colptr[k + 1]))
-                    return fail(CPK_ERR_ARG, "internal: fill pattern is not closed (column %d, row %d)", k, i);
-                std::vector<int> &o = opl[pos[i]];
-                o.push_back(id_ij); o.push_back(id_kj); o.push_back(nnzL + j);
-                ++nops;
-            }
-        }
-        if (nops > 60000000) return fail(CPK_ERR_UNSUPPORTED, "device factorization plan exceeds 6e7 products: keep the host factorization for this system");
-        // levels: the diagonal node first, then the column below it
-        int l = 0;
-        for (size_t t = 0; t < opl[nnzL + k].size(); t += 3) l = std::max(l, lev[opl[nnzL + k][t]] + 1);
-        lev[nnzL + k] = l;
-        for (int64_t q = P->colptr[k]; q < P->colptr[k + 1]; ++q) {
-            int lq = l + 1;
-            for (size_t t = 0; t < opl[q].size(); t += 3) lq = std::max(lq, std::max(lev[opl[q][t]], lev[opl[q][t + 1]]) + 1);
-            lev[q] = lq;
-        }
-    }
-    P->nops = nops;
-    int nlev = 0;
-    for (int e = 0; e < ne; ++e) nlev = std::max(nlev, lev[e] + 1);
-    P->nlev = nlev;
-    H->levptr.assign(nlev + 1, 0);
-    for (int e = 0; e < ne; ++e) H->levptr[lev[e] + 1]++;
-    for (int l = 0; l < nlev; ++l) H->levptr[l + 1] += H->levptr[l];
-    H->exec.resize(ne);
-    {
-        std::vector<int> nxt(H->levptr.begin(), H->levptr.end() - 1);
-        for (int e = 0; e < ne; ++e) H->exec[nxt[lev[e]]++] = e;
-    }
-    H->opptr.assign(ne + 1, 0);
-    for (int e = 0; e < ne; ++e) H->opptr[e + 1] = H->opptr[e] + (int)(opl[e].size() / 3);
-    H->ops.resize((size_t)3 * nops);
-    for (int e = 0; e < ne; ++e) std::copy(opl[e].begin(), opl[e].end(), H->ops.begin() + (size_t)3 * H->opptr[e]);
-    return CPK_OK;
-}
 
 // one CTA: node values from the new matrix entries, then level after level, then the scatter
 // of the factor into the compact-walk stream (ns = 0: no scatter)

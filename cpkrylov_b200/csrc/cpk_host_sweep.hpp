@@ -1,0 +1,188 @@
+// cpk_host_sweep.hpp -- item list of the LDL' sweeps for the global-memory walks
+// Host-side part of libcpk_b200 (included by cpk_host.cu only; uses its fail() and the
+// constants of cpk_device.cuh).
+#pragma once
+
+// ---------------------------------------------------------------------------
+// LDL' sweep builder.  Produces the unified item list of DevSweep: forward items
+// (level order), then backward items (level order), with the rows that need no
+// work compiled away (see cpk_device.cuh) and the segment table that tells the
+// kernel how to deal items to warps (blocks of consecutive items for bulk
+// levels, one item per warp for chains).
+// ---------------------------------------------------------------------------
+struct HSweep {
+    int nitems = 0, nfwd = 0;
+    std::vector<int> seg, levptr, sptr, col, rid, pidx, flags, partner;
+    std::vector<double> val, d, e, dp;
+    int64_t n_trivial = 0, n_fused = 0, tail_f = 0, tail_b = 0, n_warprow = 0, max_len = 0;
+    int lev_f_eff = 0, lev_b_eff = 0;
+};
+
+struct SweepRow { int row; int level; int len; };
+constexpr int kLongRow = 8;         // rows with more entries are walked by a whole warp
+typedef std::vector<std::pair<int, double>> EncRow;     // (column code, value), in accumulation order
+
+// Appends the rows (already filtered) of one direction.  `entries(r)` returns the
+// encoded dependency list of LDL row r.
+// Items of a level are created sorted by cost (long rows first).  Deal them
+// round-robin to the `nw` warps that will walk the level and store every
+// warp's hand contiguously: each warp still streams a contiguous range, and
+// every range holds the same mix of expensive and cheap items.
+static void deal_level(HSweep &W, int first, int n, int nw)
+{
+    if (n <= 1 || nw <= 1) return;
+    std::vector<int> order;             // new position -> old item (relative)
+    order.reserve(n);
+    // warp w gets [n*w/nw, n*(w+1)/nw): fill these ranges by dealing
+    std::vector<std::vector<int>> hand(std::min(nw, n));
+    const int nh = (int)hand.size();
+    // ranges have sizes that differ by at most one; deal so that range sizes match
+    std::vector<int> cap(nh);
+    for (int w = 0; w < nh; ++w) cap[w] = (int)((long long)n * (w + 1) / nh) - (int)((long long)n * w / nh);
+    int w = 0;
+    for (int i = 0; i < n; ++i) {
+        int tries = 0;
+        while ((int)hand[w].size() >= cap[w] && tries < nh) { w = (w + 1) % nh; ++tries; }
+        hand[w].push_back(i);
+        w = (w + 1) % nh;
+    }
+    for (auto &h : hand) for (int i : h) order.push_back(i);
+    // rebuild the item arrays of this level in the new order
+    const int s0 = W.sptr[first];
+    std::vector<int> col, sptr(1, s0), rid, pidx, flags, partner;
+    std::vector<double> val, d, e, dp;
+    for (int k = 0; k < n; ++k) {
+        const int it = first + order[k];
+        const int b = W.sptr[it], en = W.sptr[it + 1];
+        col.insert(col.end(), W.col.begin() + b, W.col.begin() + en);
+        val.insert(val.end(), W.val.begin() + b, W.val.begin() + en);
+        sptr.push_back(s0 + (int)col.size());
+        for (int l = 0; l < 32; ++l) {
+            const size_t sl = (size_t)it * 32 + l;
+            rid.push_back(W.rid[sl]); pidx.push_back(W.pidx[sl]); flags.push_back(W.flags[sl]); partner.push_back(W.partner[sl]);
+            d.push_back(W.d[sl]); e.push_back(W.e[sl]); dp.push_back(W.dp[sl]);
+        }
+    }
+    std::copy(col.begin(), col.end(), W.col.begin() + s0);
+    std::copy(val.begin(), val.end(), W.val.begin() + s0);
+    for (int k = 0; k <= n; ++k) W.sptr[first + k] = sptr[k];
+    const size_t base = (size_t)first * 32;
+    std::copy(rid.begin(), rid.end(), W.rid.begin() + base);
+    std::copy(pidx.begin(), pidx.end(), W.pidx.begin() + base);
+    std::copy(flags.begin(), flags.end(), W.flags.begin() + base);
+    std::copy(partner.begin(), partner.end(), W.partner.begin() + base);
+    std::copy(d.begin(), d.end(), W.d.begin() + base);
+    std::copy(e.begin(), e.end(), W.e.begin() + base);
+    std::copy(dp.begin(), dp.end(), W.dp.begin() + base);
+}
+
+template <class Entries, class Flags>
+static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vector<int64_t> &perm,
+                         const std::vector<double> &dd, const std::vector<double> &ee, const std::vector<int> &partner,
+                         int grid_warps, Entries entries, Flags flags_of)
+{
+    // the team shape that will walk this system: whole grid for large N, one CTA otherwise
+    const int deal_warps = (int)perm.size() > 24576 ? grid_warps : kWarpsPerCta;
+    // inside a level any order is valid: group rows of equal (short) length and
+    // order them by their index in the user vector, so that the P' gather and the
+    // P scatter of consecutive lanes touch consecutive addresses
+    for (auto &rw : rows) W.max_len = std::max<int64_t>(W.max_len, rw.len);
+    std::stable_sort(rows.begin(), rows.end(), [&](const SweepRow &a, const SweepRow &b) {
+        if (a.level != b.level) return a.level < b.level;
+        const int la = std::min(a.len, kLongRow + 1), lb = std::min(b.len, kLongRow + 1);
+        if (la != lb) return la > lb;
+        return perm[a.row] < perm[b.row];
+    });
+    if (W.sptr.empty()) W.sptr.push_back(0);
+    // items per level
+    std::vector<std::pair<int, int>> level_items;       // (first item, count) per level, in order
+    size_t i0 = 0;
+    while (i0 < rows.size()) {
+        const int lev = rows[i0].level;
+        const int first_item = W.nitems;
+        while (i0 < rows.size() && rows[i0].level == lev) {
+            if (rows[i0].len > kLongRow) {
+                // one long row = one item, entries spread over the 32 lanes
+                const int r = rows[i0].row;
+                const EncRow er = entries(r);
+                const size_t width = (er.size() + 31) / 32;
+                const size_t base = W.col.size();
+                W.col.resize(base + width * 32, -1);
+                W.val.resize(base + width * 32, 0.0);
+                for (size_t jx = 0; jx < er.size(); ++jx) { W.col[base + jx] = er[jx].first; W.val[base + jx] = er[jx].second; }
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (lane == 0) {
+                        W.rid.push_back(r); W.pidx.push_back((int)perm[r]); W.flags.push_back(flags_of(r) | F_WARPROW); W.d.push_back(dd[r]);
+                        if (partner[r] >= 0) { W.partner.push_back(partner[r]); W.e.push_back(ee[std::min(r, partner[r])]); W.dp.push_back(dd[partner[r]]); }
+                        else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
+                    } else {
+                        W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
+                        W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
+                    }
+                }
+                W.sptr.push_back((int)W.col.size());
+                W.nitems++; W.n_warprow++;
+                ++i0;
+                continue;
+            }
+            size_t i1 = i0;
+            while (i1 < rows.size() && i1 - i0 < 32 && rows[i1].level == lev && rows[i1].len <= kLongRow) ++i1;
+            int width = 0;
+            for (size_t t = i0; t < i1; ++t) width = std::max(width, rows[t].len);
+            const size_t base = W.col.size();
+            W.col.resize(base + (size_t)width * 32, -1);
+            W.val.resize(base + (size_t)width * 32, 0.0);
+            for (int lane = 0; lane < 32; ++lane) {
+                const size_t t = i0 + lane;
+                if (t < i1) {
+                    const int r = rows[t].row;
+                    W.rid.push_back(r);
+                    W.pidx.push_back((int)perm[r]);
+                    W.flags.push_back(flags_of(r));
+                    W.d.push_back(dd[r]);
+                    if (partner[r] >= 0) {
+                        W.partner.push_back(partner[r]);
+                        W.e.push_back(ee[std::min(r, partner[r])]);
+                        W.dp.push_back(dd[partner[r]]);
+                    } else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
+                    const EncRow er = entries(r);
+                    for (size_t jx = 0; jx < er.size(); ++jx) {
+                        W.col[base + jx * 32 + lane] = er[jx].first;
+                        W.val[base + jx * 32 + lane] = er[jx].second;
+                    }
+                } else {
+                    W.rid.push_back(-1); W.pidx.push_back(0); W.flags.push_back(0); W.d.push_back(1.0);
+                    W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0);
+                }
+            }
+            W.sptr.push_back((int)W.col.size());
+            W.nitems++;
+            i0 = i1;
+        }
+        level_items.emplace_back(first_item, W.nitems - first_item);
+        W.levptr.push_back(first_item);
+        deal_level(W, first_item, W.nitems - first_item, deal_warps);
+    }
+    // segments: a level with at least 2 items per warp is "bulk" (blocks of
+    // consecutive items per warp); runs of smaller levels
+    // are merged into one chain segment dealt round-robin.
+    int chain_first = -1, chain_end = -1;
+    auto flush_chain = [&]() {
+        if (chain_first >= 0) { W.seg.push_back(chain_first); W.seg.push_back(chain_end); W.seg.push_back(1); }
+        chain_first = -1;
+    };
+    static const double bulk_min = [] { const char *e = getenv("CPK_LDL_BULK_MIN"); return e ? atof(e) : 2.0; }();
+    static const int blk_max = [] { const char *e = getenv("CPK_LDL_BLK"); return e ? atoi(e) : 8; }();
+    for (auto &li : level_items) {
+        if (li.second >= bulk_min * grid_warps) {
+            flush_chain();
+            const int blk = std::max(1, std::min(blk_max, li.second / grid_warps));
+            W.seg.push_back(li.first); W.seg.push_back(li.first + li.second); W.seg.push_back(blk);
+        } else {
+            if (chain_first < 0) chain_first = li.first;
+            chain_end = li.first + li.second;
+        }
+    }
+    flush_chain();
+}
+
