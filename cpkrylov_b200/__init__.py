@@ -13,8 +13,8 @@ from .solvers import (cpcg, cpcglanczos, cpminres, cpsymmlq, cpgmres, cpdqgmres,
                       reg_cpkrylov, reg_solve_on, SolverError, SOLVERS)
 from ._lib import CpkError, CpkLibraryMissing, LIB_PATH     # noqa: F401
 from . import ldl                                              # noqa: F401
-from .matio import load_mat_system, system_from_K, solve_sequence   # noqa: F401
+from .matio import load_mat_system, system_from_K, solve_sequence, solve_ipm_sequence   # noqa: F401
 
 __all__ = ["opLDL2", "KktSystem", "cpcg", "cpcglanczos", "cpminres", "cpsymmlq", "cpgmres",
            "cpdqgmres", "reg_cpkrylov", "reg_solve_on", "SolverError", "SOLVERS", "CpkError", "CpkLibraryMissing",
-           "load_mat_system", "system_from_K", "solve_sequence"]
+           "load_mat_system", "system_from_K", "solve_sequence", "solve_ipm_sequence"]

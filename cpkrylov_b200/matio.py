@@ -24,7 +24,9 @@ import numpy as np
 import scipy.sparse as sp
 
 from .batch import BatchSolver
-from .solvers import reg_cpkrylov
+from .ldl import static_perm
+from .operators import KktSystem, opLDL2
+from .solvers import reg_cpkrylov, reg_solve_on
 
 
 def system_from_K(K, rhs, n, params=None):
@@ -96,3 +98,47 @@ def solve_sequence(method, systems, opts=None, factors=None, device=0, batch_max
         st = dict(st, solved=fl["solved"])
         xs[i], stats[i] = x, st
     return xs, stats
+
+
+def _same_pattern(a, b):
+    a, b = sp.csc_matrix(a), sp.csc_matrix(b)
+    a.sort_indices(); b.sort_indices()
+    return a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+
+
+def solve_ipm_sequence(method, systems, opts=None, device=0, perm=None):
+    """The systems of ONE interior-point run, in order (each may depend on the previous
+    solution, so they are solved one after the other): same sparsity patterns, new values.
+    The operator is built once -- numeric LDL' on the GPU with a static fill-reducing
+    permutation (SQD systems, opLDL2.m:81-82 does a fresh `ldl` per system) -- and refreshed in
+    place for every further system (`opLDL2.refactor`, `KktSystem.update`).
+
+    `systems` may be any iterable (e.g. a generator fed by the optimizer).  Yields
+    (x, stats, flag) per system; stats["t_setup"] is the set-up time of that system."""
+    import time
+    M = S = None
+    first = None
+    try:
+        for s in systems:
+            t0 = time.perf_counter()
+            if S is None:
+                first = s
+                if perm is None:
+                    perm = static_perm(sp.bmat([[s["G"], s["B"].T], [s["B"], -sp.csc_matrix(s["C"])]], format="csc"))
+                M = opLDL2(s["G"], s["B"], -sp.csc_matrix(s["C"]), factors="device", perm=perm, device=device)
+                S = KktSystem(s["H"], s["C"], M)
+            else:
+                for key in ("H", "B", "C", "G"):
+                    if not _same_pattern(first[key], s[key]):
+                        raise ValueError("solve_ipm_sequence: block %s changed its sparsity pattern" % key)
+                M.refactor(s["G"], s["B"], -sp.csc_matrix(s["C"]))
+                S.update(s["H"], s["C"])
+            t_setup = time.perf_counter() - t0
+            x, st, fl = reg_solve_on(S, method, s["rhs"], opts)
+            st["t_setup"] = t_setup
+            yield x, st, fl
+    finally:
+        if S is not None:
+            S.close()
+        elif M is not None:
+            M.close()

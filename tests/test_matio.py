@@ -84,3 +84,25 @@ def test_sequence_of_ipm_systems_one_launch():
         xo, so, fo = orc.reg_cpkrylov("cpminres", s["rhs"], s["H"], s["B"], s["C"], s["G"], dict(EX_OPTS), factor=lambda K, f=fac: f)
         assert st["solved"] == fo["solved"] and abs(st["niters"] - so["niters"]) <= 2
         assert relerr(x, xo) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_ipm_sequence_in_place():
+    """Generator-driven sequence: operator built once on the device, refreshed in place."""
+    from cpkrylov_b200.synth import ipm_batch_system, kp_matrix
+    from cpkrylov_b200.ldl import ldl_superlu
+    from oracle import cpk_oracle as orc
+    base = load_system("cvxqp1_m")
+    seq = [ipm_batch_system(base, j) for j in range(3)]
+    out = list(matio.solve_ipm_sequence("cpminres", (w for w in seq), dict(EX_OPTS)))
+    assert len(out) == 3
+    for j, (w, (x, st, fl)) in enumerate(zip(seq, out)):
+        fac = ldl_superlu(kp_matrix(w))
+        xo, so, fo = orc.reg_cpkrylov("cpminres", w["rhs"], w["H"], w["B"], w["C"], w["G"], dict(EX_OPTS), factor=lambda K, f=fac: f)
+        assert fl["solved"] == fo["solved"] and abs(st["niters"] - so["niters"]) <= 2
+        assert relerr(x, xo) <= 1e-7
+        if j:
+            assert st["t_setup"] < 0.05
+    bad = dict(seq[1]); bad["B"] = sp.csc_matrix(seq[1]["B"].shape)
+    with pytest.raises(ValueError):
+        list(matio.solve_ipm_sequence("cpminres", [seq[0], bad], dict(EX_OPTS)))
