@@ -103,7 +103,8 @@ struct DevSweep {
 //           kind 0          : nothing
 //           CW_BARRIER (same in all 16 slots of a step): __syncthreads after the step
 //                             -- a dependency level ends
-// tgt/col index the shared vector sv[2N] (w = sv[0..N), y = sv[N..2N)), col -1 = padding.
+// tgt/col index the shared vector sv (w = sv[0..N), y = sv[yoff..yoff+N), see DevCompact.yoff),
+// col -1 = padding.
 constexpr int kCwBlock = 16384;     // bytes per stream block
 constexpr int kCwStages = 3;        // ring depth
 constexpr int CW_ROWS2 = 1, CW_ROWS = 2, CW_WARPROW = 3, CW_DCHUNK = 4;
@@ -111,12 +112,14 @@ constexpr int CW_BARRIER = 16;
 struct DevCompact {
     int nblk;                       // 0: no stream was built
     int smem_off;                   // byte offset of the walk's region in dynamic shared memory, < 0: walk off
+    int yoff;                       // y lives at sv[yoff + i]: 0 = ONE shared vector, updated in place (w, then
+                                    // D^-1 w, then y: possible when D is diagonal), N = separate w and y (2x2 pivots)
     const unsigned char *stream;    // [nblk * kCwBlock]
     const int *perm;                // [N] w_i = z[perm_i]
 };
-__host__ __device__ inline size_t cw_smem_bytes(int N)
+__host__ __device__ inline size_t cw_smem_bytes(int N, bool one_vector)
 {
-    return (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16 + (size_t)16 * N;
+    return (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16 + (size_t)(one_vector ? 8 : 16) * N;
 }
 
 struct DevLdl {

@@ -644,7 +644,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     const char *cenv = getenv("CPK_LDL_COMPACT");
     const bool compact_walk = g_force_compact ||
                               (!use_grid(N) && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)) &&
-                               cw_smem_bytes(N) <= (size_t)dc->max_dsm);
+                               cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm);
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
@@ -823,6 +823,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // one-CTA team: compact walk (sweep values in shared memory, factor streamed through a
     // shared-memory ring) whenever its region can fit next to a solver's scratch
     m.cw.nblk = 0; m.cw.smem_off = -1; m.cw.stream = nullptr; m.cw.perm = nullptr;
+    m.cw.yoff = n2 == 0 ? 0 : N;        // diagonal D: one shared vector, updated in place
     CwStream cws;
     {
         // (below ~24 levels the level walk's two barriers-with-L2-round-trips per level cost less
@@ -830,7 +831,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
         if (compact_walk) {
             cw_sweep(cws, N, Lrows, lf, nlf, 0, 0);         // w_i -= L(i,:) w        target w_i,  deps w
             cw_dpass(cws, N, d, e, partner);                // y = D^-1 w
-            cw_sweep(cws, N, Lcols, lb, nlb, N, N);         // y_i -= L(:,i)' y       target y_i,  deps y
+            cw_sweep(cws, N, Lcols, lb, nlb, m.cw.yoff, m.cw.yoff);      // y_i -= L(:,i)' y       target y_i,  deps y
             cws.flush();
             std::vector<int> p32(N);
             for (int i = 0; i < N; ++i) p32[i] = (int)p[i];
@@ -875,7 +876,7 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     }
     if (getenv("CPK_VERBOSE") && m.cw.nblk)
         fprintf(stderr, "[cpk] compact walk: %d blocks of %d B, %lld levels in %lld steps, %lld items, shared memory %zu B\n",
-                m.cw.nblk, kCwBlock, cws.n_levels, cws.n_steps, cws.n_items, cw_smem_bytes(N));
+                m.cw.nblk, kCwBlock, cws.n_levels, cws.n_steps, cws.n_items, cw_smem_bytes(N, n2 == 0));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));      // uploads done (pageable sources are still alive here)
     *out = register_obj(std::move(o));
     return CPK_OK;
@@ -894,7 +895,8 @@ extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int
     CwStream cws;
     cw_sweep(cws, N, HL.Lrows, HL.lf, HL.nlf, 0, 0);
     cw_dpass(cws, N, HL.d, HL.e, HL.partner);
-    cw_sweep(cws, N, HL.Lcols, HL.lb, HL.nlb, N, N);
+    const int yoff = HL.n2 == 0 ? 0 : N;
+    cw_sweep(cws, N, HL.Lcols, HL.lb, HL.nlb, yoff, yoff);
     cws.flush();
     *nbytes = (int64_t)cws.bytes.size();
     if (buf && cap >= *nbytes) memcpy(buf, cws.bytes.data(), cws.bytes.size());
@@ -977,8 +979,8 @@ int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, con
     DeviceCtx *dc;
     int rc = get_device_ctx(device, &dc);
     if (rc) return rc;
-    if (N64 >= INT32_MAX || use_grid((int)N64) || cw_smem_bytes((int)N64) > (size_t)dc->max_dsm)
-        return fail(CPK_ERR_UNSUPPORTED, "device factorization serves the one-CTA team (N <= ~11000); larger systems bring host factors to cpk_ldl2_create");
+    if (N64 >= INT32_MAX || use_grid((int)N64) || cw_smem_bytes((int)N64, true) > (size_t)dc->max_dsm)
+        return fail(CPK_ERR_UNSUPPORTED, "device factorization serves the one-CTA team (N <= ~22000); larger systems bring host factors to cpk_ldl2_create");
     const int N = (int)N64, nA = (int)A->nrows;
     CUDA_TRY(cudaSetDevice(device));
     auto P = std::make_unique<SqdPlan>();
@@ -1026,7 +1028,7 @@ int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, con
         CwStream ids;
         cw_sweep(ids, N, HL.Lrows, HL.lf, HL.nlf, 0, 0);
         cw_dpass(ids, N, HL.d, HL.e, HL.partner);
-        cw_sweep(ids, N, HL.Lcols, HL.lb, HL.nlb, N, N);
+        cw_sweep(ids, N, HL.Lcols, HL.lb, HL.nlb, 0, 0);        // diagonal D: one shared vector
         ids.flush();
         if ((int)(ids.bytes.size() / kCwBlock) != M->d.cw.nblk) { cpk_destroy(h); return fail(CPK_ERR_ARG, "internal: twin stream differs in size"); }
         std::vector<int> spos, ssrc;
@@ -1230,7 +1232,7 @@ static int cw_place(const DeviceCtx *dc, const DevLdl &m, bool grid, size_t dsm,
 {
     if (grid || m.cw.nblk == 0) return -1;
     const size_t off = (dsm + 127) & ~(size_t)127;
-    const size_t need = off + cw_smem_bytes(m.N);
+    const size_t need = off + cw_smem_bytes(m.N, m.cw.yoff == 0);
     if (need > (size_t)dc->max_dsm) return -1;
     *total = std::max(*total, need);
     return (int)off;

@@ -443,7 +443,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
 
 // ---------------------------------------------------------------------------
 // Compact walk (one-CTA team): see DevCompact.  Shared-memory region:
-//   [ring: kCwStages x kCwBlock][mbarrier x kCwStages][ring entries consumed so far][sv: 2N doubles]
+//   [ring: kCwStages x kCwBlock][mbarrier x kCwStages][ring entries consumed so far][sv: N or 2N doubles]
 // The ring never stops: entry k holds stream block k mod nblk, and as soon as the
 // CTA is done with an entry the block kCwStages further on is requested, also
 // across the end of a solve -- the next solve finds its first blocks in place.
@@ -573,7 +573,7 @@ __device__ __forceinline__ void cw_rows(const CwTask &I, double *sv, int lane)
 
 // D chunk, rows 32*warp + lane of it: y_i = w_i / d_i, or the 2x2 solve with the partner
 // row (opLDL2.m:86, inv(op.D))
-__device__ __forceinline__ void cw_dchunk(const CwTask &I, double *sv, int N, int warp, int lane)
+__device__ __forceinline__ void cw_dchunk(const CwTask &I, double *sv, int yoff, int warp, int lane)
 {
     const int r = 32 * warp + lane, cnt = I.width;
     if (r >= cnt) return;
@@ -591,7 +591,7 @@ __device__ __forceinline__ void cw_dchunk(const CwTask &I, double *sv, int N, in
             y = (dp[r] * w - e[r] * wp) / det;
         }
     }
-    sv[N + I.z + r] = y;
+    sv[yoff + I.z + r] = y;
 }
 
 template <class Team>
@@ -633,7 +633,7 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
         bool synced = false;
         for (int st = 0; st < nsteps; ++st) {
             const int4 tk = slot[min(st + 1, nsteps - 1) * kWarpsPerCta];    // next slot: its latency hides behind the arithmetic
-            if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, N, warp, lane);
+            if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, C.yoff, warp, lane);
             else if (cur.kind != 0) cw_rows(cur, W.sv, lane);
             synced = cur.barrier;
             if (st + 1 < nsteps) cw_fetch(cur, blk, tk, lane);
@@ -653,10 +653,10 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
 #pragma unroll
             for (int u = 0; u < 8; ++u) ov[u] = (pi[u] >= 0) ? out[pi[u]] : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = ov[u] + W.sv[N + i0 + u * T.nthreads];
+            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = ov[u] + W.sv[C.yoff + i0 + u * T.nthreads];
         } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = W.sv[N + i0 + u * T.nthreads];
+            for (int u = 0; u < 8; ++u) if (pi[u] >= 0) out[pi[u]] = W.sv[C.yoff + i0 + u * T.nthreads];
         }
     }
     if (T.tid == 0) *W.count = k0 + (unsigned)nblk;

@@ -158,7 +158,7 @@ int  cpk_ldl2_info(cpk_handle M, int64_t *nnz_L_off, int64_t *levels_fwd, int64_
  * diagonal D) the library factorizes on the device with a STATIC permutation:
  * perm[k] = original index of row k of the permuted matrix, chosen once for fill
  * (e.g. the column permutation of a first host factorization).  One-CTA systems only
- * (N <= ~11 000); A and C bring both triangles, as MATLAB stores them. */
+ * (N <= ~22 000); A and C bring both triangles, as MATLAB stores them. */
 int  cpk_ldl2_create_sqd(cpk_handle *M, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
                          const int64_t *perm, int device);
 /* next system of the sequence: new values, SAME sparsity patterns (entry order included).

@@ -43,7 +43,7 @@ def _stream(L, d, e, perm):
     return buf
 
 
-def _run_slot(blk, slot, warp, sv, N, written):
+def _run_slot(blk, slot, warp, sv, yoff, written):
     """One slot of a step; `written` = sv indices produced since the last barrier: nothing
     in the same dependency level may read or rewrite them."""
     off, y, z, _ = (int(v) for v in slot)
@@ -71,7 +71,7 @@ def _run_slot(blk, slot, warp, sv, N, written):
         rows = np.arange(i0 + lo, i0 + hi)
         w = gather(rows)
         if not has2:
-            publish(N + rows, w / dd[lo:hi])
+            publish(yoff + rows, w / dd[lo:hi])
             return 0
         o = off + 8 * n
         ee = blk[o:o + 8 * n].view(np.float64); o += 8 * n
@@ -84,7 +84,7 @@ def _run_slot(blk, slot, warp, sv, N, written):
             else:
                 det = dd[r] * dp[r] - ee[r] * ee[r]
                 out[r - lo] = (dp[r] * w[r - lo] - ee[r] * gather(np.array([pr[r]]))[0]) / det
-        publish(N + rows, out)
+        publish(yoff + rows, out)
         return 0
     S = stride
     assert off % 16 == 0 and 1 <= S <= 32
@@ -113,11 +113,14 @@ def _run_slot(blk, slot, warp, sv, N, written):
     return 1
 
 
-def _walk(buf, N, perm, z):
+def _walk(buf, N, perm, z, yoff=None):
     """Emulation of ldl_solve_compact: per block a table of steps x 16 warp slots; the slots
-    of the steps between two barriers form one dependency level and must be independent."""
+    of the steps between two barriers form one dependency level and must be independent.
+    yoff: where y lives in the shared vector (0: one vector updated in place -- diagonal D;
+    N: separate w and y -- 2x2 pivots); default = what the builder chooses for a diagonal D."""
     assert buf.size % BLK == 0 and buf.size > 0
-    sv = np.zeros(2 * N)
+    yoff = 0 if yoff is None else yoff
+    sv = np.zeros(N + yoff)
     sv[:N] = z[perm]
     stats = dict(blocks=buf.size // BLK, steps=0, items=0, barriers=0)
     written = set()
@@ -131,14 +134,14 @@ def _walk(buf, N, perm, z):
             flags = table[st, :, 1] & CW_BARRIER
             assert flags.min() == flags.max(), "barrier flag differs between the warps of a step"
             for w in range(NW):
-                stats["items"] += _run_slot(blk, table[st, w], w, sv, N, written)
+                stats["items"] += _run_slot(blk, table[st, w], w, sv, yoff, written)
             stats["steps"] += 1
             if flags[0]:
                 stats["barriers"] += 1
                 written.clear()
     assert not written                  # the last step ends with a barrier
     y = np.zeros(N)
-    y[perm] = sv[N:]
+    y[perm] = sv[yoff:yoff + N]
     return y, stats
 
 
@@ -170,7 +173,7 @@ def test_stream_walk_equals_direct_solve_on_fixtures(cpk_lib, name, kind):
     rng = np.random.default_rng(5)
     z = rng.standard_normal(N)
     buf = _stream(L, d, e, perm)
-    y, st = _walk(buf, N, perm, z)
+    y, st = _walk(buf, N, perm, z, yoff=N if np.any(e) else 0)
     ref = _direct(L, d, e, perm, z)
     assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref), st
     # and it really inverts K_P
@@ -186,7 +189,7 @@ def test_stream_walk_small_random(cpk_lib, seed):
     for fac in (ldl_superlu, ldl_dense_bk):
         L, d, e, perm = fac(KP)
         z = np.random.default_rng(seed).standard_normal(s["N"])
-        y, st = _walk(_stream(L, d, e, perm), s["N"], np.asarray(perm), z)
+        y, st = _walk(_stream(L, d, e, perm), s["N"], np.asarray(perm), z, yoff=s["N"] if np.any(e) else 0)
         assert np.linalg.norm(KP @ y - z) <= 1e-8 * np.linalg.norm(z), (fac.__name__, st)
 
 

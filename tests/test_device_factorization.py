@@ -171,7 +171,7 @@ def test_refactor_error_paths():
         M.refactor(Gz, s["A"], -s["C"])
     assert "pivot" in str(ei.value) or "pattern" in str(ei.value)
     # after a refactorization the factor only lives in the compact-walk stream: a solver whose
-    # scratch leaves no room for it must fail loudly (cpdqgmres mem=140 needs ~170 KB of shared memory)
+    # scratch leaves no room for it must fail loudly (checked below on the larger fixture)
     M.refactor(s["G"], s["A"], -s["C"])
     S = KktSystem(s["Q"], s["C"], M)
     try:
@@ -179,8 +179,16 @@ def test_refactor_error_paths():
         xo, so, fo = orc.reg_cpkrylov("cpgmres", s["rhs"], s["Q"], s["A"], s["C"], s["G"], dict(EX_OPTS, restart=100),
                                       factor=lambda K: ldl_superlu(KP))
         assert fl["solved"] == fo["solved"] and abs(st["niters"] - so["niters"]) <= 2 and relerr(x, xo) <= 1e-7
-        with pytest.raises(_lib.CpkError) as ei:
-            cp.reg_solve_on(S, "cpdqgmres", s["rhs"], dict(EX_OPTS, mem=140))
-        assert "compact-walk stream" in str(ei.value)
     finally:
         S.close()
+    # ... on the larger fixture: 92 KB of stream region + 141 KB of cpdqgmres(128) scratch do not fit
+    s1 = load_system("cvxqp1_m")
+    M1 = cp.opLDL2(s1["G"], s1["A"], -s1["C"], factors="device", perm=static_perm(kp_of(s1)))
+    M1.refactor(s1["G"], s1["A"], -s1["C"])
+    S1 = KktSystem(s1["Q"], s1["C"], M1)
+    try:
+        with pytest.raises(_lib.CpkError) as ei:
+            cp.reg_solve_on(S1, "cpdqgmres", s1["rhs"], dict(EX_OPTS, mem=128))
+        assert "compact-walk stream" in str(ei.value)
+    finally:
+        S1.close()
