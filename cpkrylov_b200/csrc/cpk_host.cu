@@ -195,6 +195,9 @@ struct Ldl2 : Object {
     double *d_z = nullptr, *d_y = nullptr;
     DevStatus *d_status = nullptr;
     bool in_system = false;
+    bool prefer_grid = false;           // team of a single-system launch (cost model at create time)
+    int walk_deep = 0;                  // effective sweep depth > 24: a grid team takes the sync-free walk
+    int sync_free_env = -1;             // CPK_LDL_SYNCFREE at create time (-1: not set)
     // device-side numeric factorization (cpk_ldl2_create_sqd / cpk_ldl2_refactor)
     std::unique_ptr<struct SqdPlan> plan;
     bool sweep_stale = false;           // after a refactorization only the compact stream holds the new factor
@@ -344,6 +347,28 @@ static bool use_grid(int N)
     return N > thr;
 }
 
+// Team of a SINGLE-system launch.  Measured per-iteration times (cpminres, example options,
+// kkt_lap3d patterns, `scripts/team_crossover.py`):
+//   shallow sweeps (k=2, tail inversion collapses them):  grid flat ~50 us for N = 1 250 .. 24 600;
+//     one CTA 38 / 54 / 94 / 138 / 205 / 295 / 595 us at N = 1 250 / 2 160 / 4 218 / 7 290 / 11 576 / 17 280 / 24 603
+//   deep sweeps (k=6 windowed, 182 / 268 / 514 levels): one CTA with the compact walk 235 / 469 / 1 029 us,
+//     grid (sync-free walk) 932 / 1 376 / 2 633 us
+// i.e. one CTA ~ 20 + 0.016 N (+ 1.2 per level when the compact walk is needed), grid ~ 55 for sweeps
+// the tail inversion flattens (<= 48 levels here) and ~ 50 + 5 per level otherwise.
+// Batches keep the size rule (use_grid): there one SM per system is the point.
+static bool model_prefers_grid(int N, int levels, bool compact_fits)
+{
+    if (const char *e = getenv("CPK_TEAM")) {
+        if (!strcmp(e, "grid")) return true;
+        if (!strcmp(e, "cta")) return false;
+    }
+    if (use_grid(N)) return true;
+    const double cta = 20.0 + 0.016 * N + ((levels > 24 && compact_fits) ? 1.2 * levels : (levels > 24 ? 4.6 * levels : 0.0));
+    const double grid = levels <= 48 ? 55.0 : 50.0 + 5.0 * levels;
+    return grid < cta;
+}
+static bool team_is_grid(const Ldl2 *M);
+
 // ===========================================================================
 // kernels
 // ===========================================================================
@@ -478,6 +503,22 @@ k_sqd_factor(int ne, int nlev, const double *vals_in, const int *asrc, const int
         __syncthreads();
     }
     for (int t = threadIdx.x; t < ns; t += blockDim.x) stream[spos[t]] = fval[ssrc[t]];
+}
+
+static bool team_is_grid(const Ldl2 *M)
+{
+    if (const char *e = getenv("CPK_TEAM")) {
+        if (!strcmp(e, "grid")) return true;
+        if (!strcmp(e, "cta")) return false;
+    }
+    if (M->plan) return false;          // device-factorized operators live in the compact-walk stream
+    return use_grid(M->d.N) || M->prefer_grid;
+}
+// LDL' walk of one launch: a grid team facing a deep sweep polls tagged values instead of paying a
+// grid barrier per level (k=6 windowed stress system, 278+261 levels: 29 ms vs 54 ms per solve)
+static void set_walk(DevLdl &d, const Ldl2 *M, bool grid)
+{
+    d.sync_free = M->sync_free_env >= 0 ? M->sync_free_env : (grid && M->walk_deep ? 1 : 0);
 }
 
 // ===========================================================================
@@ -642,9 +683,10 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // (a solver scratch too large for the stream's shared memory): no tail inversion for it,
     // which is most of the host-side set-up time of a small system
     const char *cenv = getenv("CPK_LDL_COMPACT");
+    const bool compact_fits = !use_grid(N) && cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm;
+    const bool prefer_grid = !g_force_compact && model_prefers_grid(N, nlf + nlb, compact_fits && !(cenv && atoi(cenv) == 0));
     const bool compact_walk = g_force_compact ||
-                              (!use_grid(N) && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)) &&
-                               cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm);
+                              (compact_fits && !prefer_grid && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)));
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
@@ -818,8 +860,11 @@ int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const c
     // walk selection: one barrier per level is cheapest for shallow sweeps (and keeps the
     // one-CTA team free of polling); a grid team facing a deep sweep uses the sync-free walk
     // (measured on the k=6 windowed stress system, 278+261 levels: 29 ms vs 54 ms per solve)
-    m.sync_free = (use_grid(N) && W.lev_f_eff + W.lev_b_eff > 24) ? 1 : 0;
-    if (getenv("CPK_LDL_SYNCFREE")) m.sync_free = atoi(getenv("CPK_LDL_SYNCFREE"));
+    // (decided per launch, see set_walk: the same operator may run on either team)
+    o->prefer_grid = prefer_grid;
+    o->walk_deep = W.lev_f_eff + W.lev_b_eff > 24;
+    o->sync_free_env = getenv("CPK_LDL_SYNCFREE") ? atoi(getenv("CPK_LDL_SYNCFREE")) : -1;
+    m.sync_free = 0;
     // one-CTA team: compact walk (sweep values in shared memory, factor streamed through a
     // shared-memory ring) whenever its region can fit next to a solver's scratch
     m.cw.nblk = 0; m.cw.smem_off = -1; m.cw.stream = nullptr; m.cw.perm = nullptr;
@@ -1263,8 +1308,10 @@ int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_st
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(M->device));
     const int N = M->d.N;
+    const bool grid = team_is_grid(M);
     DevSystem hs{};
     hs.n = M->d.nA; hs.m = M->d.nC; hs.N = N; hs.M = M->d;
+    set_walk(hs.M, M, grid);
     CUDA_TRY(cudaMemcpyAsync(M->d_sys_alone, &hs, sizeof hs, cudaMemcpyHostToDevice, dc->stream));
     const double *dz = z; double *dy = y;
     if (mem == CPK_MEM_HOST) {
@@ -1275,11 +1322,11 @@ int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_st
     CUDA_TRY(cudaMemsetAsync(d_st, 0, sizeof(DevStatus), dc->stream));
     const DevSystem *ps = M->d_sys_alone;
     size_t dsm = 0;
-    int cw_off = cw_place(dc, M->d, use_grid(N), 0, &dsm);
+    int cw_off = cw_place(dc, M->d, grid, 0, &dsm);
     if (M->sweep_stale && cw_off < 0) return fail(CPK_ERR_UNSUPPORTED, "a refactorized operator only lives in the compact-walk stream, which does not fit this launch");
     void *params[] = {(void *)&ps, (void *)&dz, (void *)&dy, (void *)&d_st, (void *)&dc->ctl, (void *)&dc->partials, (void *)&cw_off};
     float ms = 0.f;
-    rc = launch_team(dc, use_grid(N), k_apply<true>, k_apply<false>, params, dsm, &ms);
+    rc = launch_team(dc, grid, k_apply<true>, k_apply<false>, params, dsm, &ms);
     if (rc) return rc;
     if (mem == CPK_MEM_HOST) CUDA_TRY(cudaMemcpy(y, M->d_y, sizeof(double) * N, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(dc->h_status, d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost));
@@ -1481,10 +1528,11 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     const int64_t cap = cpk_hist_capacity(solver, opts);
     rc = ensure_buffers(S, plan, cap);
     if (rc) return rc;
-    const bool grid = use_grid(N);
+    const bool grid = team_is_grid(S->M);
     if (grid && plan.wide_cols) { rc = ensure_wide(dc, plan.wide_cols); if (rc) return rc; }
 
     S->h.M = S->M->d;           // pick up option changes made through the opLDL2 setters
+    set_walk(S->h.M, S->M, grid);
     CUDA_TRY(cudaMemcpyAsync(S->d_sys, &S->h, sizeof(DevSystem), cudaMemcpyHostToDevice, dc->stream));
     SolveArgs a{};
     a.solver = solver; a.reg_mode = reg_mode;
@@ -1632,6 +1680,7 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
         rc = ensure_buffers(S, plan, cap);
         if (rc) return rc;
         S->h.M = S->M->d;
+        set_walk(S->h.M, S->M, q >= n_cta);
         hsys[q] = S->h;
         SolveArgs a{};
         a.solver = solver; a.reg_mode = 1;
