@@ -14,7 +14,7 @@ import numpy as np
 import scipy.sparse as sp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpk_b200.so")
+LIB_PATH = os.environ.get("CPK_LIB_PATH") or os.path.join(_HERE, "libcpk_b200.so")    # override: A/B runs of two builds
 CSRC = os.path.join(_HERE, "csrc")
 
 CPK_OK = 0

@@ -483,7 +483,9 @@ struct CtaTeam {
     }
 };
 
-#define TEAM_FOR(T, i, N) for (int i = (T).tid; i < (N); i += (T).nthreads)
+// (the team object lives in the kernel's frame and is passed by reference through non-inlined
+// calls, so its fields are local-memory loads: read the stride once per loop)
+#define TEAM_FOR(T, i, N) for (int i = (T).tid, i##_stride = (T).nthreads; i < (N); i += i##_stride)
 
 // Element-wise team loop over N elements with NIN input vectors:
 //   body(i, v) with v[k] = src[k][i]

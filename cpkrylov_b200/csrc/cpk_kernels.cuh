@@ -33,6 +33,7 @@ struct PhaseClock {
 template <class Team, class Epi>
 __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
+    const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
     // range are one contiguous span, walked in chunks of 8 entries per lane with
     // the next chunk's loads issued before the current chunk's x-gathers are
@@ -41,11 +42,11 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
     int sa, sb;
     {
         const int *split = A.wsplit[Team::kKind];
-        if (split != nullptr && A.nws[Team::kKind] == T.nwarps) {
-            sa = __ldg(&split[T.gwarp]); sb = __ldg(&split[T.gwarp + 1]);
+        if (split != nullptr && A.nws[Team::kKind] == nwarps) {
+            sa = __ldg(&split[gwarp]); sb = __ldg(&split[gwarp + 1]);
         } else {
-            sa = (int)((long long)A.nslices * T.gwarp / T.nwarps);
-            sb = (int)((long long)A.nslices * (T.gwarp + 1) / T.nwarps);
+            sa = (int)((long long)A.nslices * gwarp / nwarps);
+            sb = (int)((long long)A.nslices * (gwarp + 1) / nwarps);
         }
     }
     if (sa < sb) {
@@ -54,14 +55,14 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
         const int kb = __ldg(&A.sptr[sb]);
         int send = __ldg(&A.sptr[s + 1]);
         int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-        int row = __ldg(&A.rowmap[s * 32 + T.lane]);
-        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+        int row = __ldg(&A.rowmap[s * 32 + lane]);
+        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
         constexpr int U = 8;            // entries per lane in flight (x2: current + prefetched chunk)
         int cc[U]; double vv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int kk = k + 32 * u + T.lane;
+            const int kk = k + 32 * u + lane;
             if (kk < kb) { cc[u] = __ldg(&A.col[kk]); vv[u] = __ldg(&A.val[kk]); } else { cc[u] = 0; vv[u] = 0.0; }
         }
         while (k < kb) {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
             const int k2 = k + 32 * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int kk = k2 + 32 * u + T.lane;
+                const int kk = k2 + 32 * u + lane;
                 if (kk < kb) { cn[u] = __ldg(&A.col[kk]); vn[u] = __ldg(&A.val[kk]); } else { cn[u] = 0; vn[u] = 0.0; }
             }
 #pragma unroll
@@ -83,7 +84,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
                         acc = 0.0; ++s;
                         send = send2; row = row2;
                         send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
                     }
                     acc += vv[u] * xv[u];
                 }
@@ -96,17 +97,17 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
             if (row >= 0) epi(row, acc);
             acc = 0.0; ++s;
             row = row2;
-            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + T.lane]) : -1;
+            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         }
     }
     // long rows: one warp per row, lane-strided partial sums + butterfly
-    for (int r = T.gwarp; r < A.nlong; r += T.nwarps) {
+    for (int r = gwarp; r < A.nlong; r += nwarps) {
         const int beg = __ldg(&A.lptr[r]), end = __ldg(&A.lptr[r + 1]);
         double acc = 0.0;
-        for (int k = beg + T.lane; k < end; k += 32) acc += __ldg(&A.lval[k]) * x[__ldg(&A.lcol[k])];
+        for (int k = beg + lane; k < end; k += 32) acc += __ldg(&A.lval[k]) * x[__ldg(&A.lcol[k])];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (T.lane == 0) epi(__ldg(&A.lrow[r]), acc);
+        if (lane == 0) epi(__ldg(&A.lrow[r]), acc);
     }
 }
 
@@ -309,11 +310,12 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
     const DevSweep &S = M.sw;
     constexpr int B = 4;
     const int Nn = M.N;
+    const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     for (int g = 0; g < S.nlev; ++g) {
         const int a = __ldg(&S.levptr[g]), b = __ldg(&S.levptr[g + 1]);
         const long long cnt = b - a;
-        int t = a + (int)(cnt * T.gwarp / T.nwarps);
-        const int tend = a + (int)(cnt * (T.gwarp + 1) / T.nwarps);
+        int t = a + (int)(cnt * gwarp / nwarps);
+        const int tend = a + (int)(cnt * (gwarp + 1) / nwarps);
         while (t < tend) {
             const int nb = min(B, tend - t);
             // ---- stage A: row data of the whole batch -------------------------------
@@ -324,7 +326,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                 if (q < nb) {
                     beg[q] = __ldg(&S.sptr[t + q]);
                     wid[q] = __ldg(&S.sptr[t + q + 1]) - beg[q];
-                    const int slot = (t + q) * 32 + T.lane;
+                    const int slot = (t + q) * 32 + lane;
                     rid[q] = __ldg(&S.rid[slot]); pidx[q] = __ldg(&S.pidx[slot]);
                     flg[q] = __ldg(&S.flags[slot]); dd[q] = __ldg(&S.d[slot]);
                 } else { beg[q] = 0; wid[q] = 0; rid[q] = -1; pidx[q] = 0; flg[q] = 0; dd[q] = 1.0; }
@@ -337,8 +339,8 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
 #pragma unroll
                 for (int q = 0; q < B; ++q) {
                     c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
-                    if (wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + T.lane]); v0[q] = __ldg(&S.val[beg[q] + T.lane]); }
-                    if (wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + T.lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + T.lane]); }
+                    if (wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + lane]); v0[q] = __ldg(&S.val[beg[q] + lane]); }
+                    if (wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + lane]); }
                 }
                 // ---- stage B: gathers ---------------------------------------------------
                 double base[B], x0[B], x1[B];
@@ -389,8 +391,8 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                         rid0[q] = __shfl_sync(FULL, rid[q], 0); pidx0[q] = __shfl_sync(FULL, pidx[q], 0);
                         flg0[q] = __shfl_sync(FULL, flg[q], 0); d0[q] = __shfl_sync(FULL, dd[q], 0);
                         c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
-                        if (q < nb && wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + T.lane]); v0[q] = __ldg(&S.val[beg[q] + T.lane]); }
-                        if (q < nb && wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + T.lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + T.lane]); }
+                        if (q < nb && wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + lane]); v0[q] = __ldg(&S.val[beg[q] + lane]); }
+                        if (q < nb && wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + lane]); }
                     }
                     double base[B], x0[B], x1[B];
 #pragma unroll
@@ -398,7 +400,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                         base[q] = 0.0; x0[q] = 0.0; x1[q] = 0.0;
                         if (q < nb) {
                             const bool isfwd = (flg0[q] & F_FWD) != 0;
-                            if (T.lane == 0) base[q] = (isfwd || (flg0[q] & F_WDIRECT)) ? in(pidx0[q]) : M.wv[rid0[q]];
+                            if (lane == 0) base[q] = (isfwd || (flg0[q] & F_WDIRECT)) ? in(pidx0[q]) : M.wv[rid0[q]];
                             const double *depv = isfwd ? M.wv : M.yv;
                             if (c0[q] >= 0) x0[q] = (c0[q] >= Nn) ? M.wv[c0[q] - Nn] : depv[c0[q]];
                             else if (c0[q] <= -2) x0[q] = in(-c0[q] - 2);
@@ -413,7 +415,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                         if (c1[q] != -1) sum -= v1[q] * x1[q];
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-                        if (q < nb && T.lane == 0) {
+                        if (q < nb && lane == 0) {
                             const bool isfwd = (flg0[q] & F_FWD) != 0;
                             double acc = isfwd ? base[q] : base[q] / d0[q];
                             acc += sum;
@@ -428,7 +430,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                 } else {
                     for (int q = 0; q < nb; ++q) {
                         ItemMeta m; ItemChunk r;
-                        item_load(S, t + q, T.lane, m, r);
+                        item_load(S, t + q, lane, m, r);
                         item_process<false>(T, M, in, out, accumulate, 0ull, m, r);
                     }
                 }
