@@ -492,6 +492,10 @@ struct CtaTeam {
 // Loads are 16-byte (two elements) when N is even and every vector is 16-byte
 // aligned, and a thread has 4 such loads per vector in flight before the first
 // body runs: ~90 KB per SM must be in flight to cover the HBM latency.
+#ifndef CPK_TEAM_MAP_B
+#define CPK_TEAM_MAP_B 4
+#endif
+constexpr int kTmB = CPK_TEAM_MAP_B;    // batches of loads a thread has in flight in team_map
 template <int NIN, class Team, class Body>
 __device__ __forceinline__ void team_map(const Team &T, int N, const double *const (&src)[NIN], Body &&body)
 {
@@ -501,10 +505,10 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
     for (int k = 0; k < NIN; ++k) vec = vec && ((reinterpret_cast<unsigned long long>(src[k]) & 15ull) == 0);
     if (vec) {
         const int N2 = N >> 1;
-        for (int j0 = T.tid; j0 < N2; j0 += 4 * nt) {
-            double2 v[4][NIN];
+        for (int j0 = T.tid; j0 < N2; j0 += kTmB * nt) {
+            double2 v[kTmB][NIN];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kTmB; ++u) {
                 const int j = j0 + u * nt;
                 if (j < N2) {
 #pragma unroll
@@ -512,7 +516,7 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kTmB; ++u) {
                 const int j = j0 + u * nt;
                 if (j < N2) {
                     double a[NIN], b[NIN];
@@ -524,10 +528,10 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
             }
         }
     } else {
-        for (int i0 = T.tid; i0 < N; i0 += 4 * nt) {
-            double v[4][NIN];
+        for (int i0 = T.tid; i0 < N; i0 += kTmB * nt) {
+            double v[kTmB][NIN];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kTmB; ++u) {
                 const int i = i0 + u * nt;
                 if (i < N) {
 #pragma unroll
@@ -535,7 +539,7 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kTmB; ++u) {
                 const int i = i0 + u * nt;
                 if (i < N) body(i, v[u]);
             }

@@ -58,7 +58,10 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
         int row = __ldg(&A.rowmap[s * 32 + lane]);
         int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
-        constexpr int U = 8;            // entries per lane in flight (x2: current + prefetched chunk)
+#ifndef CPK_SPMV_U
+#define CPK_SPMV_U 8
+#endif
+        constexpr int U = CPK_SPMV_U;   // entries per lane in flight (x2: current + prefetched chunk)
         int cc[U]; double vv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -308,7 +311,10 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                                               PhaseClock *dbg = nullptr)
 {
     const DevSweep &S = M.sw;
-    constexpr int B = 4;
+#ifndef CPK_SWEEP_B
+#define CPK_SWEEP_B 4
+#endif
+    constexpr int B = CPK_SWEEP_B;
     const int Nn = M.N;
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     for (int g = 0; g < S.nlev; ++g) {
