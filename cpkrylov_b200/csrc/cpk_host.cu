@@ -526,6 +526,16 @@ static void set_walk(DevLdl &d, const Ldl2 *M, bool grid)
 // ===========================================================================
 // (C linkage comes from the declarations in cpk_b200.h)
 
+// no C++ exception crosses the C ABI: the entry points that allocate on the host run inside this
+template <class F>
+static int guarded(F &&f)
+{
+    try { return f(); }
+    catch (const std::bad_alloc &) { return fail(CPK_ERR_ALLOC, "out of host memory"); }
+    catch (const std::exception &e) { return fail(CPK_ERR_ARG, "internal error: %s", e.what()); }
+    catch (...) { return fail(CPK_ERR_ARG, "internal error"); }
+}
+
 int cpk_version(void) { return 100; }
 
 int cpk_device_count(void)
@@ -630,7 +640,7 @@ static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, in
 // ---------------------------------------------------------------------------
 static thread_local bool g_force_compact = false;   // set by cpk_ldl2_create_sqd around its call of cpk_ldl2_create
 
-int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
+static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
                     const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
 {
     if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create: null output handle");
@@ -1014,7 +1024,7 @@ static int sqd_upload_values(DeviceCtx *dc, SqdPlan *P, const cpk_csc *A, const 
     return CPK_OK;
 }
 
-int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int device)
+static int cpk_ldl2_create_sqd_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int device)
 {
     if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create_sqd: null output handle");
     if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !perm) return fail(CPK_ERR_ARG, "Invalid number of arguments.");
@@ -1056,7 +1066,7 @@ int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, con
     cpk_csc Dc{N, N, dptr.data(), dind.data(), fval.data() + P->nnzL};
     cpk_handle h = 0;
     g_force_compact = true;
-    rc = cpk_ldl2_create(&h, A, B, C, &Lc, &Dc, perm, device);
+    rc = cpk_ldl2_create_impl(&h, A, B, C, &Lc, &Dc, perm, device);
     g_force_compact = false;
     if (rc) return rc;
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
@@ -1090,7 +1100,7 @@ int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, con
 }
 
 // new values, same patterns: numeric factorization on the device, written into the operator in place
-int cpk_ldl2_refactor(cpk_handle h, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
+static int cpk_ldl2_refactor_impl(cpk_handle h, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
 {
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M) return fail(CPK_ERR_ARG, "cpk_ldl2_refactor: not an opLDL2 handle");
@@ -1139,7 +1149,7 @@ int cpk_ldl2_get_factor(cpk_handle h, int64_t *nnz, int64_t *colptr, int64_t *ro
 }
 
 // new values of H and C (same patterns) for the mat-vecs of the solver loops
-int cpk_system_update(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
+static int cpk_system_update_impl(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
 {
     System *S = lookup<System>(h, OBJ_SYSTEM);
     if (!S) return fail(CPK_ERR_ARG, "cpk_system_update: not a system handle");
@@ -1299,7 +1309,7 @@ static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **param
     return CPK_OK;
 }
 
-int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_stats *stats)
+static int cpk_ldl2_apply_impl(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_stats *stats)
 {
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M || !z || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_apply: bad handle or null vector");
@@ -1369,7 +1379,7 @@ int cpk_ldl2_matvec(cpk_handle h, const double *b, double *y, cpk_mem mem, cpk_s
 }
 
 // ---------------------------------------------------------------------------
-int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_handle Mh)
+static int cpk_system_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_handle Mh)
 {
     if (!out) return fail(CPK_ERR_ARG, "cpk_system_create: null output handle");
     Ldl2 *M = lookup<Ldl2>(Mh, OBJ_LDL2);
@@ -1586,19 +1596,19 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
 int cpk_solve(cpk_handle S, int solver, const double *b1, const cpk_opts *opts, double *dx, double *dy, cpk_mem mem,
               cpk_stats *stats, double *hist, int64_t hist_cap)
 {
-    return do_solve(S, solver, b1, opts, dx, dy, mem, stats, hist, hist_cap, 0);
+    return guarded([&] { return do_solve(S, solver, b1, opts, dx, dy, mem, stats, hist, hist_cap, 0); });
 }
 
 int cpk_reg_solve(cpk_handle S, int solver, const double *b, const cpk_opts *opts, double *x, cpk_mem mem,
                   cpk_stats *stats, double *hist, int64_t hist_cap)
 {
-    return do_solve(S, solver, b, opts, x, nullptr, mem, stats, hist, hist_cap, 1);
+    return guarded([&] { return do_solve(S, solver, b, opts, x, nullptr, mem, stats, hist, hist_cap, 1); });
 }
 
 // ---------------------------------------------------------------------------
 // batch: one CTA per system, one launch
 // ---------------------------------------------------------------------------
-int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,
+static int cpk_batch_reg_solve_impl(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,
                         double *const *x, cpk_stats *stats, double *const *hist, int64_t hist_cap)
 {
     if (!handles || count <= 0 || !b || !x || !opts) return fail(CPK_ERR_ARG, "cpk_batch_reg_solve: bad argument");
@@ -1745,6 +1755,46 @@ int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, co
     }
     if (first_rc) { g_err = first_msg; return first_rc; }
     return CPK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// guarded public entry points
+// ---------------------------------------------------------------------------
+int cpk_ldl2_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
+                    const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
+{
+    return guarded([&] { return cpk_ldl2_create_impl(out, A, B, C, L, D, perm, device); });
+}
+
+int cpk_ldl2_create_sqd(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int device)
+{
+    return guarded([&] { return cpk_ldl2_create_sqd_impl(out, A, B, C, perm, device); });
+}
+
+int cpk_ldl2_refactor(cpk_handle h, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
+{
+    return guarded([&] { return cpk_ldl2_refactor_impl(h, A, B, C); });
+}
+
+int cpk_system_update(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
+{
+    return guarded([&] { return cpk_system_update_impl(h, A, C); });
+}
+
+int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_handle Mh)
+{
+    return guarded([&] { return cpk_system_create_impl(out, A, C, Mh); });
+}
+
+int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,
+                        double *const *x, cpk_stats *stats, double *const *hist, int64_t hist_cap)
+{
+    return guarded([&] { return cpk_batch_reg_solve_impl(handles, count, solver, b, opts, x, stats, hist, hist_cap); });
+}
+
+int cpk_ldl2_apply(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_stats *stats)
+{
+    return guarded([&] { return cpk_ldl2_apply_impl(h, z, y, mem, stats); });
 }
 
 int cpk_destroy(cpk_handle h)
