@@ -493,14 +493,18 @@ struct CtaTeam {
 // aligned, and a thread has 4 such loads per vector in flight before the first
 // body runs: ~90 KB per SM must be in flight to cover the HBM latency.
 #ifndef CPK_TEAM_MAP_B
-#define CPK_TEAM_MAP_B 4
+#define CPK_TEAM_MAP_B 1
 #endif
 constexpr int kTmB = CPK_TEAM_MAP_B;    // batches of loads a thread has in flight in team_map
 template <int NIN, class Team, class Body>
 __device__ __forceinline__ void team_map(const Team &T, int N, const double *const (&src)[NIN], Body &&body)
 {
     const int nt = T.nthreads;
+#ifdef CPK_TEAM_MAP_SCALAR
+    bool vec = false;
+#else
     bool vec = (N & 1) == 0;
+#endif
 #pragma unroll
     for (int k = 0; k < NIN; ++k) vec = vec && ((reinterpret_cast<unsigned long long>(src[k]) & 15ull) == 0);
     if (vec) {
