@@ -7,8 +7,12 @@
 
 namespace cpk {
 
-constexpr int kBlock      = 512;    // threads per CTA: 1 CTA per SM, <=128 regs/thread (no spills in the streaming loops)
+#ifndef CPK_BLOCK
+#define CPK_BLOCK 512
+#endif
+constexpr int kBlock      = CPK_BLOCK;    // threads per CTA: 1 CTA per SM, <=128 regs/thread (no spills in the streaming loops)
 constexpr int kWarpsPerCta = kBlock / 32;
+constexpr int kCtasPerSm  = 512 / kBlock;     // 16 warps per SM either way
 constexpr int kRedMax     = 8;      // values reduced together in one team reduction
 constexpr unsigned FULL   = 0xffffffffu;
 

@@ -288,7 +288,7 @@ static int get_device_ctx(int device, DeviceCtx **out)
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
-    c->grid_blocks = c->num_sms;    // one CTA per SM
+    c->grid_blocks = c->num_sms * kCtasPerSm;      // 16 warps per SM
     if (const char *e = getenv("CPK_GRID_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= c->num_sms * per_sm) c->grid_blocks = v; }
     g_grid_warps_hint = c->grid_blocks * kWarpsPerCta;
     {
@@ -373,7 +373,7 @@ static bool team_is_grid(const Ldl2 *M);
 // kernels
 // ===========================================================================
 template <bool GRID>
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
 k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl *ctl, double *partials, int cw_off)
 {
     __shared__ TeamShared sh;
@@ -430,7 +430,7 @@ k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st, TeamCtl
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
 k_matvec(DevSell A, const double *x, double *y)
 {
     if (GRID) {
@@ -443,7 +443,7 @@ k_matvec(DevSell A, const double *x, double *y)
 }
 
 // debug: latency of the team barrier and of a 1-value team reduction
-__global__ void __launch_bounds__(kBlock, 1) k_barrier_bench(TeamCtl *ctl, double *partials, int iters, long long *out)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm) k_barrier_bench(TeamCtl *ctl, double *partials, int iters, long long *out)
 {
     __shared__ TeamShared sh;
     GridTeam T; T.init(ctl, partials, &sh);
@@ -482,7 +482,7 @@ Ldl2::~Ldl2() {}
 
 // one CTA: node values from the new matrix entries, then level after level, then the scatter
 // of the factor into the compact-walk stream (ns = 0: no scatter)
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
 k_sqd_factor(int ne, int nlev, const double *vals_in, const int *asrc, const int *dk, const int *exec, const int *levptr,
              const int *opptr, const int *ops, double *fval, int ns, const int *spos, const int *ssrc, double *stream, int *bad)
 {

@@ -855,7 +855,7 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
 // One persistent kernel per (solver, team kind).  GRID: cooperative launch, the
 // whole grid works on sys[0]; otherwise CTA b works on sys[b] (batch).
 template <int SOLVER, bool GRID>
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
 k_solve(const DevSystem *sys, const SolveArgs *args, TeamCtl *ctl, double *partials, double *wide, int wide_cols, int team_ctas)
 {
     __shared__ TeamShared sh;

@@ -1,2 +1,2 @@
-for lib in TM4 b200 TM1S TM2S b200 TM4; do CPK_LIB_PATH=$PWD/cpkrylov_b200/libcpk_$lib.so python bench.py --no-cpu-baseline --steps 30 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$lib', round(d['config']['device_ms_per_step'],4), round(d['value']))"; done
-for lib in TM4 b200; do for cfg in "--solver cpminres" "--solver cpdqgmres --mem 20" "--workload kkt_convdiff --mem 20"; do CPK_LIB_PATH=$PWD/cpkrylov_b200/libcpk_$lib.so python bench.py --no-cpu-baseline --steps 10 $cfg 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$lib', '$cfg', round(d['config']['device_ms_per_step'],4), round(d['value']))"; done; done
+# A/B runs on one box: environment switches / alternative builds of the library (CPK_LIB_PATH)
+for sig in 4096 256 65536 32; do CPK_SELL_SIGMA=$sig python bench.py --no-cpu-baseline --steps 30 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('sigma $sig', round(d['config']['device_ms_per_step'],4), round(d['value']))"; done
