@@ -7,12 +7,17 @@
 
 namespace cpk {
 
+// Threads per CTA (1 CTA per SM).  Every streaming phase of the persistent kernel is bound by the
+// warps an SM has in flight, not by registers per thread: 896 threads (28 warps, 72 registers) with
+// small per-thread batches (SpMV 4 entries per lane in flight, sweep batches of 2 items) measured
+// 13 % faster on cfg 3 than 512 threads (128 registers, 8 entries, batches of 4); 768 / 832 / 960 /
+// 1024 threads and other batch sizes are slower (profiles/r1_notes.md).
 #ifndef CPK_BLOCK
-#define CPK_BLOCK 512
+#define CPK_BLOCK 896
 #endif
-constexpr int kBlock      = CPK_BLOCK;    // threads per CTA: 1 CTA per SM, <=128 regs/thread (no spills in the streaming loops)
+constexpr int kBlock      = CPK_BLOCK;
 constexpr int kWarpsPerCta = kBlock / 32;
-constexpr int kCtasPerSm  = 512 / kBlock;     // 16 warps per SM either way
+constexpr int kCtasPerSm  = kBlock >= 512 ? 1 : 512 / kBlock;
 constexpr int kRedMax     = 8;      // values reduced together in one team reduction
 constexpr unsigned FULL   = 0xffffffffu;
 
@@ -93,7 +98,7 @@ struct DevSweep {
 // dependent instruction stream is what bounds a level.  The stream is a sequence of
 // fixed-size blocks:
 //   int4  {steps in the block, 0, 0, 0}
-//   int4  slot[steps][16]   what warp w does in step s:
+//   int4  slot[steps][kWarpsPerCta]   what warp w does in step s:
 //           {data offset, kind | CW_BARRIER | width << 8 | stride << 24, z, 0}
 //           kind CW_ROWS2   : `stride` rows, one per lane, <= 2 entries each
 //                             data: per lane {int tgt, col0, col1, 0; double val0, val1}
@@ -105,7 +110,7 @@ struct DevSweep {
 //                             warp w takes rows 32w..32w+31 of the chunk
 //                             data: double d[n]; (double e[n]; double dp[n]; int partner[n])
 //           kind 0          : nothing
-//           CW_BARRIER (same in all 16 slots of a step): __syncthreads after the step
+//           CW_BARRIER (same in all slots of a step): __syncthreads after the step
 //                             -- a dependency level ends
 // tgt/col index the shared vector sv (w = sv[0..N), y = sv[yoff..yoff+N), see DevCompact.yoff),
 // col -1 = padding.

@@ -288,7 +288,7 @@ static int get_device_ctx(int device, DeviceCtx **out)
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, 0));
             if (per_sm < 1) return fail(CPK_ERR_CUDA, "solver kernel %d does not fit on an SM", sv);
         }
-    c->grid_blocks = c->num_sms * kCtasPerSm;      // 16 warps per SM
+    c->grid_blocks = c->num_sms * kCtasPerSm;      // one CTA per SM (kCtasPerSm > 1 only for experimental block sizes below 512)
     if (const char *e = getenv("CPK_GRID_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= c->num_sms * per_sm) c->grid_blocks = v; }
     g_grid_warps_hint = c->grid_blocks * kWarpsPerCta;
     {

@@ -35,7 +35,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
 {
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
-    // range are one contiguous span, walked in chunks of 8 entries per lane with
+    // range are one contiguous span, walked in chunks of U entries per lane with
     // the next chunk's loads issued before the current chunk's x-gathers are
     // consumed (register double buffering), so HBM latency is off the per-slice
     // critical path.  Slice ends come from sptr, prefetched one slice ahead.
@@ -59,7 +59,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
         int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
 #ifndef CPK_SPMV_U
-#define CPK_SPMV_U 8
+#define CPK_SPMV_U 4
 #endif
         constexpr int U = CPK_SPMV_U;   // entries per lane in flight (x2: current + prefetched chunk)
         int cc[U]; double vv[U];
@@ -301,7 +301,7 @@ __device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const 
 
 // Level-synchronous walk of the item list: one team barrier per dependency
 // level, plain 8-byte values, no polling.  Inside a level every warp owns a
-// contiguous range of items and walks it in batches of 4: all row data of the
+// contiguous range of items and walks it in batches of B: all row data of the
 // batch is requested first, then all gathers, then the arithmetic -- three
 // memory round trips per batch instead of three per item.  Items that are not
 // "simple" (rows longer than 2 entries, warp-rows, 2x2 pivots) take the generic
@@ -312,7 +312,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
 {
     const DevSweep &S = M.sw;
 #ifndef CPK_SWEEP_B
-#define CPK_SWEEP_B 4
+#define CPK_SWEEP_B 2
 #endif
     constexpr int B = CPK_SWEEP_B;
     const int Nn = M.N;

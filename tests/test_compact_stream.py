@@ -18,7 +18,7 @@ from cpkrylov_b200.ldl import ldl_dense_bk, ldl_superlu
 from helpers import kp_of, load_factors, load_system, small_kkt
 
 BLK = 16384
-NW = 16                              # warps per CTA = slots per step
+NW = 28                              # warps per CTA (kBlock = 896) = slots per step
 CW_ROWS2, CW_ROWS, CW_WARPROW, CW_DCHUNK = 1, 2, 3, 4
 CW_BARRIER = 16
 
@@ -128,7 +128,7 @@ def _walk(buf, N, perm, z, yoff=None):
         blk = buf[b * BLK:(b + 1) * BLK]
         i32 = blk.view(np.int32)
         nsteps = int(i32[0])
-        assert nsteps >= 1 and 16 + 256 * nsteps <= BLK
+        assert nsteps >= 1 and 16 + 16 * NW * nsteps <= BLK
         table = i32[4:4 + 4 * NW * nsteps].reshape(nsteps, NW, 4)
         for st in range(nsteps):
             flags = table[st, :, 1] & CW_BARRIER
