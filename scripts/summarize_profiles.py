@@ -32,7 +32,7 @@ with open(os.path.join(P, tag + "_k_solve_cpcg_ncu_summary.md"), "w") as f:
     f.write("Command (on the B200 box, after the same command exited 0 without ncu):\n\n```\nncu --set full --clock-control none --import-source on "
             "-k regex:k_solve -s 3 -c 1 -o %s_k_solve_cpcg python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n```\n\n" % tag)
     f.write("Kernel: `cpk::k_solve<0, true>` = cpcg, the whole solve (21 iterations, 23 preconditioner applies) of BASELINE cfg 3 in ONE "
-            "cooperative launch, 148 CTAs x 512 threads.\n\n| metric | value | unit |\n|---|---|---|\n")
+            "cooperative launch, 148 CTAs x 896 threads.\n\n| metric | value | unit |\n|---|---|---|\n")
     for k in keys:
         if k in d:
             f.write("| `%s` | %s | %s |\n" % (k, d[k], units.get(k, '')))
