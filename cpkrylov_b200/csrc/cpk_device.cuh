@@ -98,7 +98,7 @@ struct DevSweep {
 // dependent instruction stream is what bounds a level.  The stream is a sequence of
 // fixed-size blocks:
 //   int4  {steps in the block, 0, 0, 0}
-//   int4  slot[steps][kWarpsPerCta]   what warp w does in step s:
+//   int4  slot[steps][kCwWarps]   what warp w does in step s:
 //           {data offset, kind | CW_BARRIER | width << 8 | stride << 24, z, 0}
 //           kind CW_ROWS2   : `stride` rows, one per lane, <= 2 entries each
 //                             data: per lane {int tgt, col0, col1, 0; double val0, val1}
@@ -116,6 +116,8 @@ struct DevSweep {
 // col -1 = padding.
 constexpr int kCwBlock = 16384;     // bytes per stream block
 constexpr int kCwStages = 3;        // ring depth
+constexpr int kCwWarps = 16;        // warps that walk the stream = slots per step (the CTA may have more)
+static_assert(kCwWarps <= kWarpsPerCta, "compact walk: not enough warps in a CTA");
 constexpr int CW_ROWS2 = 1, CW_ROWS = 2, CW_WARPROW = 3, CW_DCHUNK = 4;
 constexpr int CW_BARRIER = 16;
 struct DevCompact {

@@ -973,7 +973,7 @@ static void cw_value_map(const std::vector<unsigned char> &ids, std::vector<int>
         const int nsteps = *reinterpret_cast<const int *>(blk);
         const int *slot = reinterpret_cast<const int *>(blk + 16);
         std::vector<int> seen;              // D chunks are shared by the 16 slots of their step
-        for (int t = 0; t < nsteps * kWarpsPerCta; ++t) {
+        for (int t = 0; t < nsteps * kCwWarps; ++t) {
             const int off = slot[4 * t], y = slot[4 * t + 1];
             const int kind = y & 15, width = (y >> 8) & 0xffff, stride = (y >> 24) & 0xff;
             if (kind == 0) continue;

@@ -20,17 +20,17 @@ struct CwStream {
     std::vector<unsigned char> bytes;       // finished blocks
     int nblk = 0;
     // block under construction
-    std::vector<int> table;                 // 4 ints per slot, kWarpsPerCta slots per step
+    std::vector<int> table;                 // 4 ints per slot, kCwWarps slots per step
     std::vector<unsigned char> blob;
     long long n_levels = 0, n_steps = 0, n_items = 0;
     int rot = 0;                            // first warp of the next step (rotates, so that the warp
                                             // busy in one step is rarely the one busy in the next)
     size_t used(size_t more_steps, size_t more_bytes) const {
-        return 16 + 4 * table.size() + 16 * kWarpsPerCta * more_steps + blob.size() + more_bytes;
+        return 16 + 4 * table.size() + 16 * kCwWarps * more_steps + blob.size() + more_bytes;
     }
     void flush() {
         if (table.empty()) return;
-        const size_t nsteps = table.size() / (4 * kWarpsPerCta);
+        const size_t nsteps = table.size() / (4 * kCwWarps);
         const size_t area = 16 + 4 * table.size();
         std::vector<unsigned char> blk(kCwBlock, 0);
         int *h = reinterpret_cast<int *>(blk.data());
@@ -45,8 +45,8 @@ struct CwStream {
         ++nblk;
         table.clear(); blob.clear();
     }
-    // appends one step (a row of kWarpsPerCta empty slots) and returns its first slot
-    size_t new_step() { table.resize(table.size() + 4 * kWarpsPerCta, 0); ++n_steps; return table.size() - 4 * kWarpsPerCta; }
+    // appends one step (a row of kCwWarps empty slots) and returns its first slot
+    size_t new_step() { table.resize(table.size() + 4 * kCwWarps, 0); ++n_steps; return table.size() - 4 * kCwWarps; }
     void set_slot(size_t step0, int w, int off, const CwItemH &it) {
         int *sl = &table[step0 + 4 * w];
         sl[0] = off; sl[1] = it.kind | (it.width << 8) | (it.stride << 24); sl[2] = it.z;
@@ -57,9 +57,9 @@ struct CwStream {
         ++n_items;
         return off;
     }
-    void barrier_after(size_t step0) { for (int w = 0; w < kWarpsPerCta; ++w) table[step0 + 4 * w + 1] |= CW_BARRIER; }
+    void barrier_after(size_t step0) { for (int w = 0; w < kCwWarps; ++w) table[step0 + 4 * w + 1] |= CW_BARRIER; }
     // One dependency level (or the D pass): its items run concurrently, a CTA barrier
-    // closes it.  More than kWarpsPerCta items take several steps, only the last has the barrier.
+    // closes it.  More than kCwWarps items take several steps, only the last has the barrier.
     void level(const std::vector<CwItemH> &items) {
         if (items.empty()) return;
         ++n_levels;
@@ -69,7 +69,7 @@ struct CwStream {
                 if (used(1, it.data.size()) > (size_t)kCwBlock) flush();
                 st = new_step();
                 const int off = put_data(it);
-                for (int w = 0; w < kWarpsPerCta; ++w) if (32 * w < it.width) set_slot(st, w, off, it);
+                for (int w = 0; w < kCwWarps; ++w) if (32 * w < it.width) set_slot(st, w, off, it);
             }
             barrier_after(st);
             return;
@@ -78,12 +78,12 @@ struct CwStream {
         while (i < items.size()) {
             if (used(1, items[i].data.size()) > (size_t)kCwBlock) flush();      // the level continues in the next block
             st = new_step();
-            for (int q = 0; q < kWarpsPerCta && i < items.size(); ++q) {
+            for (int q = 0; q < kCwWarps && i < items.size(); ++q) {
                 if (used(0, items[i].data.size()) > (size_t)kCwBlock) break;
-                set_slot(st, (rot + q) % kWarpsPerCta, put_data(items[i]), items[i]);
+                set_slot(st, (rot + q) % kCwWarps, put_data(items[i]), items[i]);
                 ++i;
             }
-            rot = (rot + 5) % kWarpsPerCta;
+            rot = (rot + 5) % kCwWarps;
         }
         barrier_after(st);
     }

@@ -629,28 +629,35 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
     }
     __syncthreads();
     lap(0);
-    for (int b = 0; b < nblk; ++b) {
-        const unsigned k = k0 + (unsigned)b;
-        if (!W.wait(T, k)) return;
-        lap(1);
-        const unsigned char *blk = W.ring + (size_t)(k % kCwStages) * kCwBlock;
-        const int nsteps = *reinterpret_cast<const int *>(blk);
-        const int4 *slot = reinterpret_cast<const int4 *>(blk + 16) + warp;
-        CwTask cur;
-        cw_fetch(cur, blk, slot[0], lane);
-        bool synced = false;
-        for (int st = 0; st < nsteps; ++st) {
-            const int4 tk = slot[min(st + 1, nsteps - 1) * kWarpsPerCta];    // next slot: its latency hides behind the arithmetic
-            if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, C.yoff, warp, lane);
-            else if (cur.kind != 0) cw_rows(cur, W.sv, lane);
-            synced = cur.barrier;
-            if (st + 1 < nsteps) cw_fetch(cur, blk, tk, lane);
-            if (synced) __syncthreads();
+    // The walk itself is done by the first kCwWarps warps (a level is one warp's dependent
+    // instruction stream: more warps only add barrier and issue pressure); they synchronise on a
+    // named barrier of their own, the other warps wait for them at the CTA barrier below.
+    auto walkers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(32 * kCwWarps) : "memory"); };
+    if (warp < kCwWarps) {
+        for (int b = 0; b < nblk; ++b) {
+            const unsigned k = k0 + (unsigned)b;
+            if (!W.wait(T, k)) break;           // watchdog fired: the abort flag is set, results are void
+            lap(1);
+            const unsigned char *blk = W.ring + (size_t)(k % kCwStages) * kCwBlock;
+            const int nsteps = *reinterpret_cast<const int *>(blk);
+            const int4 *slot = reinterpret_cast<const int4 *>(blk + 16) + warp;
+            CwTask cur;
+            cw_fetch(cur, blk, slot[0], lane);
+            bool synced = false;
+            for (int st = 0; st < nsteps; ++st) {
+                const int4 tk = slot[min(st + 1, nsteps - 1) * kCwWarps];   // next slot: its latency hides behind the arithmetic
+                if (cur.kind == CW_DCHUNK) cw_dchunk(cur, W.sv, C.yoff, warp, lane);
+                else if (cur.kind != 0) cw_rows(cur, W.sv, lane);
+                synced = cur.barrier;
+                if (st + 1 < nsteps) cw_fetch(cur, blk, tk, lane);
+                if (synced) walkers_sync();
+            }
+            if (!synced) walkers_sync();        // every walker is done with this ring entry
+            if (T.tid == 0) W.issue(C, k + (unsigned)kCwStages);
+            lap(2);
         }
-        if (!synced) __syncthreads();           // every warp is done with this ring entry
-        if (T.tid == 0) W.issue(C, k + (unsigned)kCwStages);
-        lap(2);
     }
+    __syncthreads();
     // out = P * y
     for (int i0 = T.tid; i0 < N; i0 += 8 * T.nthreads) {
         int pi[8];
