@@ -116,7 +116,10 @@ struct DevSweep {
 // col -1 = padding.
 constexpr int kCwBlock = 16384;     // bytes per stream block
 constexpr int kCwStages = 3;        // ring depth
-constexpr int kCwWarps = 16;        // warps that walk the stream = slots per step (the CTA may have more)
+#ifndef CPK_CW_WARPS
+#define CPK_CW_WARPS 16
+#endif
+constexpr int kCwWarps = CPK_CW_WARPS;      // warps that walk the stream = slots per step (the CTA may have more)
 static_assert(kCwWarps <= kWarpsPerCta, "compact walk: not enough warps in a CTA");
 constexpr int CW_ROWS2 = 1, CW_ROWS = 2, CW_WARPROW = 3, CW_DCHUNK = 4;
 constexpr int CW_BARRIER = 16;

@@ -180,7 +180,7 @@ static void cw_dpass(CwStream &S, int N, const std::vector<double> &d, const std
     std::vector<CwItemH> items;
     for (int i0 = 0; i0 < N;) {
         bool has2 = false;
-        int cnt = std::min(512, N - i0);
+        int cnt = std::min(32 * kCwWarps, N - i0);      // one row per walker thread
         for (int r = 0; r < cnt; ++r) has2 = has2 || partner[i0 + r] >= 0;
         if (has2) cnt = std::min(cnt, 256);
         CwItemH it{CW_DCHUNK, cnt, has2 ? 1 : 0, i0, {}};
