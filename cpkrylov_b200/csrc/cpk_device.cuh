@@ -117,10 +117,14 @@ struct DevSweep {
 constexpr int kCwBlock = 16384;     // bytes per stream block
 constexpr int kCwStages = 3;        // ring depth
 #ifndef CPK_CW_WARPS
-#define CPK_CW_WARPS 16
+#define CPK_CW_WARPS 12
 #endif
 constexpr int kCwWarps = CPK_CW_WARPS;      // warps that walk the stream = slots per step (the CTA may have more)
 static_assert(kCwWarps <= kWarpsPerCta, "compact walk: not enough warps in a CTA");
+#ifndef CPK_BATCH_BLOCK
+#define CPK_BATCH_BLOCK 448
+#endif
+constexpr int kBatchBlock = CPK_BATCH_BLOCK;   // threads per CTA of a batch launch with more systems than SMs: two CTAs share an SM
 constexpr int CW_ROWS2 = 1, CW_ROWS = 2, CW_WARPROW = 3, CW_DCHUNK = 4;
 constexpr int CW_BARRIER = 16;
 struct DevCompact {

@@ -1717,7 +1717,15 @@ static int cpk_batch_reg_solve_impl(const cpk_handle *handles, int64_t count, in
         const DevSystem *d_sys = dc->d_bsys; const SolveArgs *d_args = dc->d_bargs;
         double *nullp = nullptr; int zero = 0;
         void *params[] = {(void *)&d_sys, (void *)&d_args, (void *)&dc->ctl, (void *)&nullp, (void *)&nullp, (void *)&zero, (void *)&zero};
-        CUDA_TRY(cudaLaunchKernel(solver_kernel(solver, false), dim3((unsigned)n_cta), dim3(kBlock), params, dsm_total, dc->stream));
+        // A batch wants throughput, not the latency of one system: with fewer threads per CTA two CTAs
+        // share an SM (registers and shared memory allow it), and the level-bound LDL' walks of the two
+        // systems overlap.  The walkers of the compact walk must all be there.
+        // (256 systems of the cvxqp1 pattern: 23.4 ms with 896 threads per CTA, 17.7 ms with 448, 18.7 ms
+        // with 384; batches that leave SMs idle keep the full CTA)
+        static const int batch_env = [] { const char *e = getenv("CPK_BATCH_BLOCK"); return e ? atoi(e) : 0; }();
+        int batch_block = batch_env > 0 ? batch_env : (n_cta > dc->num_sms ? kBatchBlock : kBlock);
+        batch_block = std::max(32 * kCwWarps, std::min(kBlock, (batch_block + 31) & ~31));
+        CUDA_TRY(cudaLaunchKernel(solver_kernel(solver, false), dim3((unsigned)n_cta), dim3(batch_block), params, dsm_total, dc->stream));
         ++launches;
     }
     const int per_wave = std::max(1, dc->grid_blocks / tc);

@@ -18,7 +18,7 @@ from cpkrylov_b200.ldl import ldl_dense_bk, ldl_superlu
 from helpers import kp_of, load_factors, load_system, small_kkt
 
 BLK = 16384
-NW = 16                              # warps that walk the stream (kCwWarps) = slots per step
+NW = 12                              # warps that walk the stream (kCwWarps) = slots per step
 CW_ROWS2, CW_ROWS, CW_WARPROW, CW_DCHUNK = 1, 2, 3, 4
 CW_BARRIER = 16
 
