@@ -35,13 +35,21 @@ class BatchSolver:
 
     def solve(self, method, rhs, opts=None):
         cnt = len(self.systems)
+        if len(rhs) != cnt:
+            raise ValueError("batch of %d systems got %d right-hand sides" % (cnt, len(rhs)))
         name = method if isinstance(method, str) else method.cpk_name
-        n, m = self.systems[0].n, self.systems[0].m
+        # ONE option set serves the whole launch: the defaults that depend on the size (itmax = n
+        # resp. n + m, cpcg.m:99, cpgmres.m:105) are taken from the LARGEST system of the batch
+        n = max(S.n for S in self.systems)
+        m = max(S.m for S in self.systems)
         sid, o = _fill_opts(name, opts, n, m)
         L = _lib.lib()
         cap = int(L.cpk_hist_capacity(sid, ct.byref(o)))
         handles = (ct.c_uint64 * cnt)(*[S.handle.value for S in self.systems])
-        bs = [np.ascontiguousarray(b, dtype=np.float64) for b in rhs]
+        bs = [np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1)) for b in rhs]
+        for i, (b, S) in enumerate(zip(bs, self.systems)):
+            if b.size != S.N:
+                raise ValueError("right-hand side %d has %d entries, system %d has N = %d" % (i, b.size, i, S.N))
         xs = [np.empty(S.N) for S in self.systems]
         hs = [np.zeros((3, cap)) for _ in range(cnt)]
         bp = (ct.c_void_p * cnt)(*[b.ctypes.data for b in bs])

@@ -50,6 +50,55 @@ struct DevSell {
     const double *lval;
 };
 
+// ---------------------------------------------------------------------------
+// Row-class layout ("RC") for passes over SHORT rows with a heavy per-row epilogue: the levels
+// of a shallow LDL' sweep and the refinement residual x - K_P*y.  The rows of one pass (level)
+// are sorted by their entry count; class w holds the rows with exactly w entries as a dense
+// rectangle
+//     rowmap[ngroups*32], d[ngroups*32], col[w][ngroups*32], val[w][ngroups*32]
+// (rows of a class in ascending row order, last group padded with rowmap = -1).  No slice
+// pointers and no padding entries: every address a row needs follows from its position, so a
+// thread issues ALL streamed loads of a batch of rows at once (one round trip), then all
+// gathers (second round trip) -- the walk over SELL items needs three dependent trips and
+// 20 bytes of per-lane item metadata.  Rows with more than `maxw` entries form a CSR list of
+// their own (one warp per row).
+// A level is a run of pieces (one per class present).  Its batches (a few consecutive groups of
+// one piece) are dealt round robin to the warps of the team, computed on the fly from the piece
+// table -- no per-team split arrays: such a pass is bound by dependent round trips per warp, so
+// the warps must walk equal numbers of batches, not equal numbers of bytes.
+// ---------------------------------------------------------------------------
+struct RcPiece { int width, ngroups, row_off, ent_off; };   // width < 0: long rows (one row per group, ent_off = first row in lptr)
+constexpr int kRcInline = 40;       // pieces kept inside the descriptor (shared-memory copy); the rest is read from global memory
+constexpr int kRcMaxLev = 48;
+constexpr int RC_IDX_BITS = 28;     // row / column codes: index in the low 28 bits
+constexpr int RC_IDX_MASK = (1 << RC_IDX_BITS) - 1;
+// column codes of a sweep: source of the gathered value in bits 28-29
+constexpr int RC_SRC_Y = 0, RC_SRC_W = 1, RC_SRC_IN = 2;
+// row codes of a sweep: flags in bits 28-29 (-1 = padding lane)
+constexpr int RC_F_FUSED = 1;       // forward row whose column of L is empty: y = w/d, written to the output
+constexpr int RC_F_WDIRECT = 1;     // backward row without forward work: w = (P'z)_i read from the input
+constexpr int RC_F_STOREY = 2;      // y_i is gathered by a later level: keep it in yv
+
+struct DevRc {
+    int nlev, npieces;
+    int nfwd_lev;                   // sweeps: levels [0, nfwd_lev) are forward levels, the rest backward
+    short levp[kRcMaxLev + 2];      // [nlev+1] first piece of every level
+    RcPiece inl[kRcInline];
+    const RcPiece *pieces;          // [npieces]
+    const int    *rowmap;           // row code per position
+    const double *d;                // sweeps: D(i,i) per position; unused (nullptr) for plain matrices
+    const int    *col;
+    const double *val;
+    const int    *lptr;             // long rows
+    const int    *lcol;
+    const double *lval;
+    __device__ __forceinline__ RcPiece piece(int p) const {
+        if (p < kRcInline) return inl[p];
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(pieces) + p);
+        return RcPiece{v.x, v.y, v.z, v.w};
+    }
+};
+
 // A value and the tag (solve epoch) that says it is ready.  16-byte aligned so
 // that ld/st.relaxed.gpu.b128 moves both in one single-copy-atomic access: no
 // fence is needed between "data" and "flag" because they are the same word.
@@ -151,8 +200,12 @@ struct DevLdl {
     // level-synchronous state: plain values, a team barrier separates the levels
     double *wv, *yv;
     int    sync_free;       // 1: tagged sync-free walk, 0: one barrier per level
-    // K_P = [A B'; B C] for the refinement residual and `divide`
-    DevSell KP;
+    // row-class form of a shallow sweep (levels walked with one barrier each; wv / yv are then
+    // indexed by the USER index of a row, not by its LDL row id)
+    int    use_rc;          // 1: walk `rc` instead of the item list
+    DevRc  rc;
+    // K_P = [A B'; B C] for the refinement residual and `divide` (row-class layout, one level)
+    DevRc  KP;
     DevSell K12, K22;       // B' (nA x nC) and C (nC x nC) for the stateful residual update
     double *atycy;          // [N] = [Aty; Cy]
     double *rvec;           // [N] refinement residual

@@ -48,10 +48,29 @@ static int fail(int code, const char *fmt, ...)
 #include "cpk_host_sparse.hpp"
 #include "cpk_host_sweep.hpp"
 
+// FNV-1a over the pattern arrays (colptr, rowind) of a CSC matrix: "same sparsity pattern, entry
+// order included" is what the value-refresh entry points (cpk_ldl2_refactor, cpk_system_update)
+// rely on -- they copy new values into layouts compiled from the pattern seen at create time.
+static uint64_t pattern_hash(const cpk_csc *A)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(&A->nrows, sizeof A->nrows); mix(&A->ncols, sizeof A->ncols);
+    mix(A->colptr, sizeof(int64_t) * (size_t)(A->ncols + 1));
+    const int64_t nnz = A->colptr[A->ncols];
+    if (nnz > 0) mix(A->rowind, sizeof(int64_t) * (size_t)nnz);
+    return h;
+}
+
 // ===========================================================================
 // device objects
 // ===========================================================================
 #include "cpk_host_compact.hpp"
+constexpr int kRcSweepMaxW = 32;    // same for the rows of a sweep (tail inversion makes rows of tens of entries)
+constexpr int kRcMatMaxW = 16;      // widest row class of a plain matrix in row-class form (wider rows: one warp per row)
 
 // Device memory of one object.  Arrays come from the device's stream-ordered pool
 // (cudaMallocAsync on the legacy stream, release threshold = keep everything): a small system
@@ -89,6 +108,8 @@ struct DevArena {
         return e;
     }
 };
+
+#include "cpk_host_rc.hpp"
 
 // contiguous slice ranges per warp, balanced by padded entries (+ a per-slice cost)
 static std::vector<int> warp_split(const std::vector<int> &sptr, int nslices, int nwarps)
@@ -183,6 +204,11 @@ struct DeviceCtx {
 };
 constexpr int kMaxBatch = 4096;
 static std::mutex g_mu;
+// Every entry point that launches serialises on this lock: the per-device launch context (team
+// control block, partials, pinned status, staging buffers, stream, events) is shared by all
+// handles of a device, and a cooperative kernel owns every SM anyway.
+static std::recursive_mutex g_launch_mu;
+#define CPK_LAUNCH_LOCK() std::lock_guard<std::recursive_mutex> launch_lock__(g_launch_mu)
 static std::unordered_map<int, std::unique_ptr<DeviceCtx>> g_dev;
 static std::unordered_map<uint64_t, std::unique_ptr<Object>> g_obj;
 static uint64_t g_next = 1;
@@ -197,6 +223,10 @@ struct Ldl2 : Object {
     bool in_system = false;
     bool prefer_grid = false;           // team of a single-system launch (cost model at create time)
     int walk_deep = 0;                  // effective sweep depth > 24: a grid team takes the sync-free walk
+    uint64_t patA = 0, patB = 0, patC = 0;  // pattern hashes of the blocks of K_P at create time
+    int64_t kp_nval = 0, kp_nlval = 0; // value counts of K_P in row-class form (pattern check of the refactorization)
+    bool has_items = true;              // the item list of the sweeps was built (level / sync-free walks)
+    bool has_rc = false;                // the row-class form of the sweeps was built (shallow sweeps, diagonal D)
     int sync_free_env = -1;             // CPK_LDL_SYNCFREE at create time (-1: not set)
     // device-side numeric factorization (cpk_ldl2_create_sqd / cpk_ldl2_refactor)
     std::unique_ptr<struct SqdPlan> plan;
@@ -219,6 +249,7 @@ struct System : Object {
     double *d_work = nullptr; long long work_len = 0;
     double *d_hist = nullptr; long long hist_cap = 0;
     double *d_gs = nullptr; long long gs_len = 0;
+    uint64_t patH = 0, patC = 0;        // pattern hashes of H and C at create time
     System() { kind = OBJ_SYSTEM; }
 };
 
@@ -246,6 +277,7 @@ static const void *solver_kernel(int solver, bool grid)
 template <bool GRID> __global__ void k_apply(const DevSystem *sys, const double *z, double *y, DevStatus *st,
                                              TeamCtl *ctl, double *partials, int cw_off);
 template <bool GRID> __global__ void k_matvec(DevSell A, const double *x, double *y);
+template <bool GRID> __global__ void k_matvec_rc(const __grid_constant__ DevRc A, const double *x, double *y);
 
 static int get_device_ctx(int device, DeviceCtx **out)
 {
@@ -442,6 +474,27 @@ k_matvec(DevSell A, const double *x, double *y)
     }
 }
 
+template <bool GRID>
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
+k_matvec_rc(const __grid_constant__ DevRc A, const double *x, double *y)
+{
+    __shared__ DevRc s_A;
+    {
+        const int *src = reinterpret_cast<const int *>(&A);
+        int *dst = reinterpret_cast<int *>(&s_A);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevRc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    MatvecOp op{{}, x, y};
+    if (GRID) {
+        GridTeam T; T.init(nullptr, nullptr, nullptr);
+        rc_level(s_A, 0, T.gwarp, T.nwarps, T.lane, op);
+    } else {
+        CtaTeam T; T.init(nullptr, nullptr, nullptr);
+        rc_level(s_A, 0, T.gwarp, T.nwarps, T.lane, op);
+    }
+}
+
 // debug: latency of the team barrier and of a 1-value team reduction
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) k_barrier_bench(TeamCtl *ctl, double *partials, int iters, long long *out)
 {
@@ -474,6 +527,35 @@ extern "C" int cpk_debug_barrier_cycles(int device, int iters, double *sync_cycl
     cudaFree(d_out);
     if (sync_cycles) *sync_cycles = (double)h[0] / iters;
     if (reduce_cycles) *reduce_cycles = (double)h[1] / iters;
+    return CPK_OK;
+}
+
+// debug / test hook: util/SymGivens.m evaluated by the device function the GMRES / DQGMRES
+// loops call (all five branches are reachable: b == 0 & a == 0, b == 0, a == 0, |b| > |a|, else)
+__global__ void k_sym_givens(int n, const double *a, const double *b, double *c, double *s, double *d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sym_givens(a[i], b[i], c[i], s[i], d[i]);
+}
+extern "C" int cpk_debug_sym_givens(int device, int n, const double *a, const double *b, double *c, double *s, double *d)
+{
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+    if (n <= 0 || !a || !b || !c || !s || !d) return fail(CPK_ERR_ARG, "cpk_debug_sym_givens: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    double *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, sizeof(double) * 5 * (size_t)n));
+    CUDA_TRY(cudaMemcpy(buf, a, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(buf + n, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+    k_sym_givens<<<(n + 127) / 128, 128, 0, dc->stream>>>(n, buf, buf + n, buf + 2 * (size_t)n, buf + 3 * (size_t)n, buf + 4 * (size_t)n);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    CUDA_TRY(cudaMemcpy(c, buf + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s, buf + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(d, buf + 4 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(buf);
     return CPK_OK;
 }
 
@@ -519,6 +601,8 @@ static bool team_is_grid(const Ldl2 *M)
 static void set_walk(DevLdl &d, const Ldl2 *M, bool grid)
 {
     d.sync_free = M->sync_free_env >= 0 ? M->sync_free_env : (grid && M->walk_deep ? 1 : 0);
+    if (!M->has_items) d.sync_free = 0;
+    d.use_rc = M->has_rc && !d.sync_free;
 }
 
 // ===========================================================================
@@ -638,42 +722,24 @@ static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, in
 }
 
 // ---------------------------------------------------------------------------
-static thread_local bool g_force_compact = false;   // set by cpk_ldl2_create_sqd around its call of cpk_ldl2_create
-
-static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
-                    const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
+// The two sweeps of the LDL' solve, compiled from the parsed factors: row classification
+// (trivial / fused rows), tail inversion, then the item list (level / sync-free walks) and/or
+// the row-class form (shallow sweeps with a diagonal D).  No device needed.
+// ---------------------------------------------------------------------------
+struct SweepBuild {
+    HSweep W;
+    HRc RC;
+    bool have_rc = false, want_items = true, walk_deep = false;
+};
+static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, SweepBuild *SB)
 {
-    if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create: null output handle");
-    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !csc_ok(L) || !csc_ok(D) || !perm)
-        return fail(CPK_ERR_ARG, "Invalid number of arguments.");                   // opLDL2.m:61-63
-    if (A->nrows != A->ncols || C->nrows != C->ncols)
-        return fail(CPK_ERR_DIM, "First and last arguments must be square.");       // opLDL2.m:68-70
-    if (B->ncols != A->nrows || B->nrows != C->nrows)
-        return fail(CPK_ERR_DIM, "Incompatible dimensions.");                       // opLDL2.m:73-75
-    const int64_t nA = A->nrows, nC = C->nrows, N64 = nA + nC;
-    if (N64 >= (int64_t)1 << 30) return fail(CPK_ERR_UNSUPPORTED, "N = %lld exceeds int32 indexing", (long long)N64);
-    if (L->nrows != N64 || L->ncols != N64 || D->nrows != N64 || D->ncols != N64)
-        return fail(CPK_ERR_DIM, "LDL factors must be %lld x %lld", (long long)N64, (long long)N64);
-    const int N = (int)N64;
-    DeviceCtx *dc;
-    int rc = get_device_ctx(device, &dc);
-    if (rc) return rc;
-
-    const auto t_begin = std::chrono::steady_clock::now();
-    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    };
-    HostLdl HL;
-    rc = parse_ldl(L, D, perm, N, &HL);
-    if (rc) return rc;
-    const double t_parse = ms_since(t_begin);
     std::vector<int64_t> &p = HL.p;
     std::vector<double> &d = HL.d, &e = HL.e;
     std::vector<int> &partner = HL.partner;
     const int64_t n2 = HL.n2;
     HCsr &Lrows = HL.Lrows, &Lcols = HL.Lcols;
-    std::vector<int> &lf = HL.lf, &lb = HL.lb;
-    const int nlf = HL.nlf, nlb = HL.nlb;
+    HSweep &W = SB->W;
+    HRc &RC = SB->RC;
     // ---- classify rows and build the unified item list
     std::vector<char> hasR(N), hasC(N), triv(N), fused(N);
     for (int i = 0; i < N; ++i) {
@@ -682,7 +748,6 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
         fused[i] = hasR[i] && !hasC[i] && partner[i] < 0;       // y_i = w_i/d_i inside the forward item
     }
     if (getenv("CPK_LDL_NO_SHORTCUTS")) { std::fill(triv.begin(), triv.end(), 0); std::fill(fused.begin(), fused.end(), 0); }
-    HSweep W;
     // Depth reduction: the last levels of a sweep hold few rows but cost one
     // cross-SM hop each.  Rows of levels >= cut are rewritten by substituting
     // their in-tail dependencies (an explicit inverse of the small unit-
@@ -692,11 +757,6 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     // a system that will walk the compact stream keeps the global sweep only as a fallback
     // (a solver scratch too large for the stream's shared memory): no tail inversion for it,
     // which is most of the host-side set-up time of a small system
-    const char *cenv = getenv("CPK_LDL_COMPACT");
-    const bool compact_fits = !use_grid(N) && cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm;
-    const bool prefer_grid = !g_force_compact && model_prefers_grid(N, nlf + nlb, compact_fits && !(cenv && atoi(cenv) == 0));
-    const bool compact_walk = g_force_compact ||
-                              (compact_fits && !prefer_grid && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)));
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
     static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
@@ -725,6 +785,7 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     for (double v : Lrows.val) maxL = std::max(maxL, std::fabs(v));
     std::vector<int> levf(N, 0), levb(N, 0);
     std::unordered_map<int, EncRow> tailf, tailb;
+    std::vector<SweepRow> rowsF, rowsB;
     {
         // ---------------- forward ----------------
         for (int i = 0; i < N; ++i) {
@@ -761,25 +822,11 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
             for (auto &kv : tailf) levf[kv.first] = cut;
             break;
         }
-        std::vector<SweepRow> rows;
         for (int i = 0; i < N; ++i) {
             if (triv[i]) continue;
             auto it = tailf.find(i);
-            rows.push_back({i, levf[i], it == tailf.end() ? Lrows.len(i) : (int)it->second.size()});
+            rowsF.push_back({i, levf[i], it == tailf.end() ? Lrows.len(i) : (int)it->second.size()});
         }
-        sweep_append(W, rows, p, d, e, partner, g_grid_warps_hint,
-                     [&](int r) {
-                         auto it = tailf.find(r);
-                         if (it != tailf.end()) return it->second;
-                         EncRow er;
-                         for (int64_t k = Lrows.ptr[r]; k < Lrows.ptr[r + 1]; ++k) {
-                             const int jx = Lrows.col[k];
-                             er.emplace_back(triv[jx] ? (int)(-(p[jx]) - 2) : jx, Lrows.val[k]);
-                         }
-                         return er;
-                     },
-                     [&](int r) { return F_FWD | (fused[r] ? F_FUSED : 0); });
-        W.nfwd = W.nitems;
         W.lev_f_eff = 0;
         for (int i = 0; i < N; ++i) if (!triv[i]) W.lev_f_eff = std::max(W.lev_f_eff, levf[i] + 1);
     }
@@ -826,33 +873,152 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
             for (auto &kv : tailb) levb[kv.first] = cut;
             break;
         }
-        std::vector<SweepRow> rows;
         for (int i = 0; i < N; ++i) {
             if (fused[i]) continue;
             auto it = tailb.find(i);
-            rows.push_back({i, levb[i], it == tailb.end() ? Lcols.len(i) : (int)it->second.size()});
+            rowsB.push_back({i, levb[i], it == tailb.end() ? Lcols.len(i) : (int)it->second.size()});
         }
-        sweep_append(W, rows, p, d, e, partner, g_grid_warps_hint,
-                     [&](int r) {
-                         auto it = tailb.find(r);
-                         if (it != tailb.end()) return it->second;
-                         EncRow er;
-                         for (int64_t k = Lcols.ptr[r]; k < Lcols.ptr[r + 1]; ++k) er.emplace_back(Lcols.col[k], Lcols.val[k]);
-                         return er;
-                     },
-                     [&](int r) { return (triv[r] ? F_WDIRECT : 0) | (hasR[r] ? F_STORE : 0) | (partner[r] >= 0 ? F_PARTNER : 0); });
         W.lev_b_eff = 0;
         for (int i = 0; i < N; ++i) if (!fused[i]) W.lev_b_eff = std::max(W.lev_b_eff, levb[i] + 1);
         W.tail_f = (long long)tailf.size(); W.tail_b = (long long)tailb.size();
     }
     for (int i = 0; i < N; ++i) { W.n_trivial += triv[i]; W.n_fused += fused[i]; }
+    // encoded dependency lists of a row in the two sweeps (item-list codes: c >= 0 LDL row id,
+    // c >= N forward result of row c - N, c <= -2 input element -c-2)
+    auto entriesF = [&](int r) {
+        auto it = tailf.find(r);
+        if (it != tailf.end()) return it->second;
+        EncRow er;
+        for (int64_t k = Lrows.ptr[r]; k < Lrows.ptr[r + 1]; ++k) {
+            const int jx = Lrows.col[k];
+            er.emplace_back(triv[jx] ? (int)(-(p[jx]) - 2) : jx, Lrows.val[k]);
+        }
+        return er;
+    };
+    auto entriesB = [&](int r) {
+        auto it = tailb.find(r);
+        if (it != tailb.end()) return it->second;
+        EncRow er;
+        for (int64_t k = Lcols.ptr[r]; k < Lcols.ptr[r + 1]; ++k) er.emplace_back(Lcols.col[k], Lcols.val[k]);
+        return er;
+    };
+    // Which form(s) of the sweeps to build.  Shallow sweeps without 2x2 pivots are walked in
+    // row-class form (one pass per level); the item list is only built when a walk that needs
+    // it can be chosen: the sync-free walk (deep sweeps on a grid team, or forced through
+    // CPK_LDL_SYNCFREE), 2x2 pivots, CPK_LDL_RC=0.
+    const char *rcenv = getenv("CPK_LDL_RC");
+    const bool rc_ok = n2 == 0 && N < (1 << RC_IDX_BITS) && W.lev_f_eff + W.lev_b_eff <= kRcMaxLev && !(rcenv && atoi(rcenv) == 0);
+    const bool walk_deep = W.lev_f_eff + W.lev_b_eff > 24;
+    const bool want_items = !rc_ok || walk_deep || getenv("CPK_LDL_SYNCFREE") != nullptr || getenv("CPK_LDL_ITEMS") != nullptr;
+    bool have_rc = false;
+    if (rc_ok) {
+        // codes -> user indices.  y of a row is kept in yv only when a later backward row gathers it.
+        std::vector<char> yref(N, 0);
+        for (auto &rw : rowsB) for (auto &x : entriesB(rw.row)) if (x.first >= 0 && x.first < N) yref[x.first] = 1;
+        RC.with_d = true;
+        std::vector<RcRowIn> in;
+        in.reserve(rowsF.size());
+        // rows without any work in either sweep (y_i = z_i / d_i) ride on the forward pass, as
+        // fused rows without entries: it is the lighter of the two
+        for (auto &rw : rowsF)
+            in.push_back(RcRowIn{(int)p[rw.row] | ((fused[rw.row] ? RC_F_FUSED : 0) | (fused[rw.row] && yref[rw.row] ? RC_F_STOREY : 0)) << RC_IDX_BITS,
+                                 rw.level, rw.row, rw.len, d[rw.row]});
+        std::vector<char> lone(N, 0);
+        for (auto &rw : rowsB)
+            if (triv[rw.row] && rw.len == 0 && !yref[rw.row]) {
+                lone[rw.row] = 1;
+                in.push_back(RcRowIn{(int)p[rw.row] | (RC_F_FUSED << RC_IDX_BITS), 0, rw.row, 0, d[rw.row]});
+            }
+        const int nlf_eff = std::max(W.lev_f_eff, 1);
+        rc_append(RC, std::move(in), nlf_eff, [&](int r) {
+            EncRow er = lone[r] ? EncRow() : entriesF(r);
+            for (auto &x : er) x.first = x.first >= 0 ? ((RC_SRC_W << RC_IDX_BITS) | (int)p[x.first]) : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2));
+            return er;
+        }, kRcSweepMaxW);
+        RC.nfwd_lev = RC.nlev;
+        std::vector<RcRowIn> inb;
+        inb.reserve(rowsB.size());
+        for (auto &rw : rowsB)
+            if (!lone[rw.row])
+                inb.push_back(RcRowIn{(int)p[rw.row] | ((triv[rw.row] ? RC_F_WDIRECT : 0) | (yref[rw.row] ? RC_F_STOREY : 0)) << RC_IDX_BITS,
+                                      rw.level, rw.row, rw.len, d[rw.row]});
+        rc_append(RC, std::move(inb), W.lev_b_eff, [&](int r) {
+            EncRow er = entriesB(r);
+            for (auto &x : er)
+                x.first = x.first >= N ? ((RC_SRC_W << RC_IDX_BITS) | (int)p[x.first - N])
+                        : (x.first >= 0 ? ((RC_SRC_Y << RC_IDX_BITS) | (int)p[x.first]) : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2)));
+            return er;
+        }, kRcSweepMaxW);
+        have_rc = rc_fits(RC);
+    }
+    if (want_items || !have_rc) {
+        sweep_append(W, rowsF, p, d, e, partner, grid_warps, entriesF,
+                     [&](int r) { return F_FWD | (fused[r] ? F_FUSED : 0); });
+        W.nfwd = W.nitems;
+        sweep_append(W, rowsB, p, d, e, partner, grid_warps, entriesB,
+                     [&](int r) { return (triv[r] ? F_WDIRECT : 0) | (hasR[r] ? F_STORE : 0) | (partner[r] >= 0 ? F_PARTNER : 0); });
+    }
     if ((int64_t)W.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
+    SB->have_rc = have_rc; SB->want_items = want_items || !have_rc; SB->walk_deep = walk_deep;
+    return CPK_OK;
+}
+
+// ---------------------------------------------------------------------------
+static thread_local bool g_force_compact = false;   // set by cpk_ldl2_create_sqd around its call of cpk_ldl2_create
+
+static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C,
+                    const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int device)
+{
+    if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create: null output handle");
+    if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !csc_ok(L) || !csc_ok(D) || !perm)
+        return fail(CPK_ERR_ARG, "Invalid number of arguments.");                   // opLDL2.m:61-63
+    if (A->nrows != A->ncols || C->nrows != C->ncols)
+        return fail(CPK_ERR_DIM, "First and last arguments must be square.");       // opLDL2.m:68-70
+    if (B->ncols != A->nrows || B->nrows != C->nrows)
+        return fail(CPK_ERR_DIM, "Incompatible dimensions.");                       // opLDL2.m:73-75
+    const int64_t nA = A->nrows, nC = C->nrows, N64 = nA + nC;
+    if (N64 >= (int64_t)1 << 30) return fail(CPK_ERR_UNSUPPORTED, "N = %lld exceeds int32 indexing", (long long)N64);
+    if (L->nrows != N64 || L->ncols != N64 || D->nrows != N64 || D->ncols != N64)
+        return fail(CPK_ERR_DIM, "LDL factors must be %lld x %lld", (long long)N64, (long long)N64);
+    const int N = (int)N64;
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    HostLdl HL;
+    rc = parse_ldl(L, D, perm, N, &HL);
+    if (rc) return rc;
+    const double t_parse = ms_since(t_begin);
+    std::vector<int64_t> &p = HL.p;
+    std::vector<double> &d = HL.d, &e = HL.e;
+    std::vector<int> &partner = HL.partner;
+    const int64_t n2 = HL.n2;
+    HCsr &Lrows = HL.Lrows, &Lcols = HL.Lcols;
+    std::vector<int> &lf = HL.lf, &lb = HL.lb;
+    const int nlf = HL.nlf, nlb = HL.nlb;
+    // ---- the sweeps: item list and / or row-class form
+    const char *cenv = getenv("CPK_LDL_COMPACT");
+    const bool compact_fits = !use_grid(N) && cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm;
+    const bool prefer_grid = !g_force_compact && model_prefers_grid(N, nlf + nlb, compact_fits && !(cenv && atoi(cenv) == 0));
+    const bool compact_walk = g_force_compact ||
+                              (compact_fits && !prefer_grid && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)));
+    SweepBuild SB;
+    rc = build_sweeps(HL, N, compact_walk, g_grid_warps_hint, &SB);
+    if (rc) return rc;
+    HSweep &W = SB.W;
+    HRc &RC = SB.RC;
+    const bool have_rc = SB.have_rc, want_items = SB.want_items, walk_deep = SB.walk_deep;
     const double t_sweeps = ms_since(t_begin);
     // ---- K_P = [A B'; B C] by rows
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, (int)nA, (int)nC);
-    HSell sKP = build_sell(KP), sK12 = build_sell(Bt), sK22 = build_sell(Cr);
-    if ((int64_t)sKP.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
+    HSell sK12 = build_sell(Bt), sK22 = build_sell(Cr);
+    HRc rKP = build_rc(KP, kRcMatMaxW);
+    if (!rc_fits(rKP)) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
 
     const double t_sell = ms_since(t_begin);
     // ---- upload
@@ -862,6 +1028,10 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     DevLdl &m = o->d;
     m.N = N; m.nA = (int)nA; m.nC = (int)nC;
     CUDA_TRY(upload_sweep(o->ar, W, m.sw));
+    o->has_items = W.nitems > 0 || !have_rc;
+    o->has_rc = have_rc;
+    m.use_rc = 0;
+    if (have_rc) CUDA_TRY(upload_rc(o->ar, RC, m.rc)); else memset(&m.rc, 0, sizeof m.rc);
     CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));        // tag 0 = never produced; epochs start at 1
     CUDA_TRY(o->ar.alloc(&m.ybuf, N, true));
     CUDA_TRY(o->ar.alloc(&m.epoch, 1, true));
@@ -872,7 +1042,7 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     // (measured on the k=6 windowed stress system, 278+261 levels: 29 ms vs 54 ms per solve)
     // (decided per launch, see set_walk: the same operator may run on either team)
     o->prefer_grid = prefer_grid;
-    o->walk_deep = W.lev_f_eff + W.lev_b_eff > 24;
+    o->walk_deep = walk_deep;
     o->sync_free_env = getenv("CPK_LDL_SYNCFREE") ? atoi(getenv("CPK_LDL_SYNCFREE")) : -1;
     m.sync_free = 0;
     // one-CTA team: compact walk (sweep values in shared memory, factor streamed through a
@@ -895,7 +1065,9 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
             m.cw.nblk = cws.nblk;
         }
     }
-    CUDA_TRY(upload_sell(o->ar, sKP, m.KP));
+    CUDA_TRY(upload_rc(o->ar, rKP, m.KP));
+    o->kp_nval = (int64_t)rKP.val.size(); o->kp_nlval = (int64_t)rKP.lval.size();
+    o->patA = pattern_hash(A); o->patB = pattern_hash(B); o->patC = pattern_hash(C);
     CUDA_TRY(upload_sell(o->ar, sK12, m.K12));
     CUDA_TRY(upload_sell(o->ar, sK22, m.K22));
     CUDA_TRY(o->ar.alloc(&m.atycy, N, true));                                   // opLDL2.m:90-91
@@ -912,6 +1084,14 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
         fprintf(stderr, "[cpk] LDL sweep: N=%d trivial=%lld fused=%lld items=%d (fwd %d) segments=%d levels L %d/%d -> effective %d/%d, tail rows inverted %lld/%lld, warp-rows %lld (longest row %lld), padded entries %zu\n",
                 N, (long long)W.n_trivial, (long long)W.n_fused, W.nitems, W.nfwd, (int)W.seg.size() / 3, nlf, nlb, W.lev_f_eff, W.lev_b_eff,
                 (long long)W.tail_f, (long long)W.tail_b, (long long)W.n_warprow, (long long)W.max_len, W.col.size());
+    if (getenv("CPK_VERBOSE") && have_rc) {
+        fprintf(stderr, "[cpk] row-class sweeps: %d+%d levels, %zu pieces, %lld rows, %lld entries, %lld long rows; item list %s\n",
+                RC.nfwd_lev, RC.nlev - RC.nfwd_lev, RC.pieces.size(), (long long)RC.nrows, (long long)RC.nnz, (long long)RC.nlong,
+                want_items ? "built too" : "not built");
+        for (int l = 0; l < RC.nlev; ++l)
+            for (int q = RC.levp[l]; q < RC.levp[l + 1]; ++q)
+                fprintf(stderr, "[cpk]   level %d %s: width %d, %d groups\n", l, l < RC.nfwd_lev ? "fwd" : "bwd", RC.pieces[q].width, RC.pieces[q].ngroups);
+    }
     if (getenv("CPK_VERBOSE"))
         fprintf(stderr, "[cpk] set-up ms: parse+levels %.2f, sweeps %.2f, K_P SELL %.2f, uploads+stream %.2f\n",
                 t_parse, t_sweeps - t_parse, t_sell - t_sweeps, ms_since(t_begin) - t_sell);
@@ -956,6 +1136,50 @@ extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int
     *nbytes = (int64_t)cws.bytes.size();
     if (buf && cap >= *nbytes) memcpy(buf, cws.bytes.data(), cws.bytes.size());
     return CPK_OK;
+}
+
+// debug / test hook (no device needed): the row-class form of the sweeps of a factorization
+// (and, with L == NULL, of the plain matrix A as one level), so that the host-side builder can
+// be checked on a machine without a GPU.
+//   sizes = {have_rc, nlev, nfwd_lev, npieces, len(rowmap), len(col), len(lptr), len(lcol)}
+// Call with the arrays NULL to get the sizes.
+extern "C" int cpk_debug_rc(const cpk_csc *A, const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int64_t *sizes,
+                            int *pieces, int *levp, int *rowmap, double *d, int *col, double *val, int *lptr, int *lcol, double *lval)
+{
+    if (!sizes) return fail(CPK_ERR_ARG, "cpk_debug_rc: bad argument");
+    return guarded([&] {
+        SweepBuild SB;
+        HRc plain;
+        const HRc *R = nullptr;
+        if (L) {
+            if (!csc_ok(L) || !csc_ok(D) || !perm) return fail(CPK_ERR_ARG, "cpk_debug_rc: bad argument");
+            const int N = (int)L->nrows;
+            HostLdl HL;
+            int rc = parse_ldl(L, D, perm, N, &HL);
+            if (rc) return rc;
+            rc = build_sweeps(HL, N, false, 148 * kWarpsPerCta, &SB);
+            if (rc) return rc;
+            R = &SB.RC;
+            sizes[0] = SB.have_rc;
+        } else {
+            if (!csc_ok(A)) return fail(CPK_ERR_ARG, "cpk_debug_rc: bad argument");
+            plain = build_rc(csr_from_csc(*A), kRcMatMaxW);
+            R = &plain;
+            sizes[0] = rc_fits(plain);
+        }
+        sizes[1] = R->nlev; sizes[2] = R->nfwd_lev; sizes[3] = (int64_t)R->pieces.size(); sizes[4] = (int64_t)R->rowmap.size();
+        sizes[5] = (int64_t)R->col.size(); sizes[6] = (int64_t)R->lptr.size(); sizes[7] = (int64_t)R->lcol.size();
+        if (pieces) memcpy(pieces, R->pieces.data(), sizeof(RcPiece) * R->pieces.size());
+        if (levp) std::copy(R->levp.begin(), R->levp.end(), levp);
+        if (rowmap) std::copy(R->rowmap.begin(), R->rowmap.end(), rowmap);
+        if (d && R->with_d) std::copy(R->d.begin(), R->d.end(), d);
+        if (col) std::copy(R->col.begin(), R->col.end(), col);
+        if (val) std::copy(R->val.begin(), R->val.end(), val);
+        if (lptr) std::copy(R->lptr.begin(), R->lptr.end(), lptr);
+        if (lcol) std::copy(R->lcol.begin(), R->lcol.end(), lcol);
+        if (lval) std::copy(R->lval.begin(), R->lval.end(), lval);
+        return (int)CPK_OK;
+    });
 }
 
 // positions (in doubles) of every factor value inside a compact-walk stream, read off a twin
@@ -1026,6 +1250,7 @@ static int sqd_upload_values(DeviceCtx *dc, SqdPlan *P, const cpk_csc *A, const 
 
 static int cpk_ldl2_create_sqd_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C, const int64_t *perm, int device)
 {
+    CPK_LAUNCH_LOCK();
     if (!out) return fail(CPK_ERR_ARG, "cpk_ldl2_create_sqd: null output handle");
     if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C) || !perm) return fail(CPK_ERR_ARG, "Invalid number of arguments.");
     if (A->nrows != A->ncols || C->nrows != C->ncols) return fail(CPK_ERR_DIM, "First and last arguments must be square.");
@@ -1102,12 +1327,16 @@ static int cpk_ldl2_create_sqd_impl(cpk_handle *out, const cpk_csc *A, const cpk
 // new values, same patterns: numeric factorization on the device, written into the operator in place
 static int cpk_ldl2_refactor_impl(cpk_handle h, const cpk_csc *A, const cpk_csc *B, const cpk_csc *C)
 {
+    CPK_LAUNCH_LOCK();
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M) return fail(CPK_ERR_ARG, "cpk_ldl2_refactor: not an opLDL2 handle");
     if (!M->plan) return fail(CPK_ERR_ARG, "cpk_ldl2_refactor: the operator was not created by cpk_ldl2_create_sqd");
     if (!csc_ok(A) || !csc_ok(B) || !csc_ok(C)) return fail(CPK_ERR_ARG, "Invalid number of arguments.");
     if (A->nrows != M->d.nA || A->ncols != M->d.nA || C->nrows != M->d.nC || C->ncols != M->d.nC || B->nrows != M->d.nC || B->ncols != M->d.nA)
         return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    if (pattern_hash(A) != M->patA || pattern_hash(B) != M->patB || pattern_hash(C) != M->patC)
+        return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with "
+                                 "(same colptr and rowind arrays, entry order included)");
     DeviceCtx *dc;
     int rc = get_device_ctx(M->device, &dc);
     if (rc) return rc;
@@ -1121,10 +1350,18 @@ static int cpk_ldl2_refactor_impl(cpk_handle h, const cpk_csc *A, const cpk_csc 
     const int nA = M->d.nA, nC = M->d.nC;
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, nA, nC);
-    const HSell hs[3] = {build_sell(KP), build_sell(Bt), build_sell(Cr)};
-    const DevSell *ds[3] = {&M->d.KP, &M->d.K12, &M->d.K22};
-    for (int q = 0; q < 3; ++q) {
-        if (hs[q].nslices != ds[q]->nslices || (int)hs[q].lrow.size() != ds[q]->nlong)
+    {
+        const HRc rk = build_rc(KP, kRcMatMaxW);
+        if ((int)rk.pieces.size() != M->d.KP.npieces || (int64_t)rk.val.size() != M->kp_nval || (int64_t)rk.lval.size() != M->kp_nlval)
+            return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
+        if (!rk.val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KP.val), rk.val.data(), sizeof(double) * rk.val.size(), cudaMemcpyHostToDevice, dc->stream));
+        if (!rk.lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KP.lval), rk.lval.data(), sizeof(double) * rk.lval.size(), cudaMemcpyHostToDevice, dc->stream));
+        CUDA_TRY(cudaStreamSynchronize(dc->stream));      // rk goes out of scope
+    }
+    const HSell hs[2] = {build_sell(Bt), build_sell(Cr)};
+    const DevSell *ds[2] = {&M->d.K12, &M->d.K22};
+    for (int q = 0; q < 2; ++q) {
+        if (hs[q].nslices != ds[q]->nslices || (int)hs[q].lrow.size() != ds[q]->nlong)       // (cannot differ once the hashes agree)
             return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
         if (!hs[q].val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->val), hs[q].val.data(), sizeof(double) * hs[q].val.size(), cudaMemcpyHostToDevice, dc->stream));
         if (!hs[q].lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->lval), hs[q].lval.data(), sizeof(double) * hs[q].lval.size(), cudaMemcpyHostToDevice, dc->stream));
@@ -1151,11 +1388,15 @@ int cpk_ldl2_get_factor(cpk_handle h, int64_t *nnz, int64_t *colptr, int64_t *ro
 // new values of H and C (same patterns) for the mat-vecs of the solver loops
 static int cpk_system_update_impl(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
 {
+    CPK_LAUNCH_LOCK();
     System *S = lookup<System>(h, OBJ_SYSTEM);
     if (!S) return fail(CPK_ERR_ARG, "cpk_system_update: not a system handle");
     if (!csc_ok(A) || !csc_ok(C)) return fail(CPK_ERR_ARG, "cpk_system_update: bad matrix");
     const int n = S->h.n, m = S->h.m;
     if (A->nrows != n || A->ncols != n || C->nrows != m || C->ncols != m) return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    if (pattern_hash(A) != S->patH || pattern_hash(C) != S->patC)
+        return fail(CPK_ERR_DIM, "cpk_system_update needs the sparsity pattern the system was created with "
+                                 "(same colptr and rowind arrays, entry order included)");
     DeviceCtx *dc;
     int rc = get_device_ctx(S->device, &dc);
     if (rc) return rc;
@@ -1311,6 +1552,7 @@ static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **param
 
 static int cpk_ldl2_apply_impl(cpk_handle h, const double *z, double *y, cpk_mem mem, cpk_stats *stats)
 {
+    CPK_LAUNCH_LOCK();
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M || !z || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_apply: bad handle or null vector");
     DeviceCtx *dc;
@@ -1347,6 +1589,7 @@ static int cpk_ldl2_apply_impl(cpk_handle h, const double *z, double *y, cpk_mem
 static int run_matvec(int device, const DevSell &A, const double *x, double *y, cpk_mem mem, cpk_stats *stats,
                       double *stage_x, double *stage_y)
 {
+    CPK_LAUNCH_LOCK();
     DeviceCtx *dc;
     int rc = get_device_ctx(device, &dc);
     if (rc) return rc;
@@ -1371,11 +1614,39 @@ static int run_matvec(int device, const DevSell &A, const double *x, double *y, 
     return CPK_OK;
 }
 
+static int run_matvec_rc(int device, const DevRc &A, int n, const double *x, double *y, cpk_mem mem, cpk_stats *stats,
+                         double *stage_x, double *stage_y)
+{
+    CPK_LAUNCH_LOCK();
+    DeviceCtx *dc;
+    int rc = get_device_ctx(device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    const double *dx = x; double *dy = y;
+    if (mem == CPK_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(stage_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, dc->stream));
+        dx = stage_x; dy = stage_y;
+    }
+    CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
+    const bool grid = use_grid(n);
+    if (grid) k_matvec_rc<true><<<dc->grid_blocks, kBlock, 0, dc->stream>>>(A, dx, dy);
+    else      k_matvec_rc<false><<<1, kBlock, 0, dc->stream>>>(A, dx, dy);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    CUDA_TRY(cudaStreamSynchronize(dc->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, dc->ev0, dc->ev1));
+    if (mem == CPK_MEM_HOST) CUDA_TRY(cudaMemcpy(y, stage_y, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (stats) { memset(stats, 0, sizeof *stats); stats->t_solve_ms = ms; stats->launches = 1; }
+    return CPK_OK;
+}
+
 int cpk_ldl2_matvec(cpk_handle h, const double *b, double *y, cpk_mem mem, cpk_stats *stats)
 {
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M || !b || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_matvec: bad handle or null vector");
-    return run_matvec(M->device, M->d.KP, b, y, mem, stats, M->d_z, M->d_y);
+    return run_matvec_rc(M->device, M->d.KP, M->d.N, b, y, mem, stats, M->d_z, M->d_y);
 }
 
 // ---------------------------------------------------------------------------
@@ -1427,6 +1698,7 @@ static int cpk_system_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_c
     CUDA_TRY(o->ar.alloc(&o->d_b, d.N));
     CUDA_TRY(o->ar.alloc(&o->d_x, d.N));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+    o->patH = pattern_hash(A); o->patC = pattern_hash(C);
     M->in_system = true;
     *out = register_obj(std::move(o));
     return CPK_OK;
@@ -1523,6 +1795,7 @@ static int ensure_buffers(System *S, const Plan &p, int64_t hist_cap)
 static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *opts, double *x_out, double *dy_out,
                     cpk_mem mem, cpk_stats *stats, double *hist, int64_t hist_cap, int reg_mode)
 {
+    CPK_LAUNCH_LOCK();
     System *S = lookup<System>(h, OBJ_SYSTEM);
     if (!S) return fail(CPK_ERR_ARG, "not a system handle");
     if (!b || !x_out || !opts) return fail(CPK_ERR_ARG, "reg_cpkrylov: not enough inputs");       // reg_cpkrylov.m:122-125
@@ -1552,7 +1825,10 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
         a.b = S->d_b; a.x = S->d_x;
     } else {
         a.b = b;
-        a.x = (reg_mode || !dy_out || dy_out == x_out + n) ? x_out : S->d_x;
+        // the kernel writes all N entries [x; y]: straight into the caller's buffer only when that
+        // buffer has them (reg mode, or dy directly behind dx); otherwise through the internal
+        // N-vector, of which dx (n entries) and, if asked for, dy (m entries) are copied out
+        a.x = (reg_mode || (dy_out && dy_out == x_out + n)) ? x_out : S->d_x;
     }
     a.atol = opts->atol; a.rtol = opts->rtol; a.btol = opts->btol; a.itmax = opts->itmax;
     a.restart = plan.restart; a.mem = plan.mem; a.profile = opts->profile;
@@ -1611,6 +1887,7 @@ int cpk_reg_solve(cpk_handle S, int solver, const double *b, const cpk_opts *opt
 static int cpk_batch_reg_solve_impl(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,
                         double *const *x, cpk_stats *stats, double *const *hist, int64_t hist_cap)
 {
+    CPK_LAUNCH_LOCK();
     if (!handles || count <= 0 || !b || !x || !opts) return fail(CPK_ERR_ARG, "cpk_batch_reg_solve: bad argument");
     if (count > kMaxBatch) return fail(CPK_ERR_UNSUPPORTED, "batch larger than %d systems: split it", kMaxBatch);
     Plan plan;

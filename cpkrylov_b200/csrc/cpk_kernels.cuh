@@ -140,6 +140,10 @@ struct VecIn {
     }
 };
 
+}  // namespace cpk
+#include "cpk_rc.cuh"
+namespace cpk {
+
 struct ItemMeta { int beg, end, slot, rid, pidx, flags; double d; };
 struct ItemChunk { int c[4]; double v[4]; };
 
@@ -686,32 +690,9 @@ template <class Team>
 __device__ __forceinline__ void ldl_solve(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate, int epoch)
 {
     if (Team::kKind == 1 && M.cw.smem_off >= 0) ldl_solve_compact(T, M, in, out, accumulate);
+    else if (M.use_rc) ldl_solve_rc(T, M, in, out, accumulate);
     else if (M.sync_free) ldl_solve_syncfree(T, M, in, out, accumulate, epoch);
     else ldl_solve_levels(T, M, in, out, accumulate, (PhaseClock *)nullptr);
-}
-
-// r = xin - K*y with partial sums of r'r (and xin'xin): opLDL2.m:175-177,182-183
-struct NoRider {
-    static constexpr bool kActive = false;
-    __device__ __forceinline__ double operator()(int, double, double) const { return 0.0; }
-};
-
-// `rider(row, xin_row, y_row)` lets the caller piggy-back one more sum over the rows on
-// this pass (e.g. the P-inner product a solver needs right after the apply).
-template <class Team, class Rider>
-__device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecIn xin, const double *y,
-                                            double *r, double &rr, double &xx, bool want_xx, Rider &rider, double &extra)
-{
-    rr = 0.0; xx = 0.0; extra = 0.0;
-    spmv_sell(T, M.KP, y, [&](int row, double s) {
-        const double xi = xin(row);
-        if (xin.wb) xin.wb[row] = xi;          // pending axpy of the caller lands in memory here
-        const double ri = xi - s;
-        r[row] = ri;
-        rr += ri * ri;
-        if (want_xx) xx += xi * xi;
-        if (Rider::kActive) extra += rider(row, xi, y[row]);
-    });
 }
 
 // ---------------------------------------------------------------------------

@@ -82,8 +82,15 @@ __device__ __forceinline__ void sym_givens(double a, double b, double &c, double
 struct CgRider {
     static constexpr bool kActive = true;
     const double *X, *PQ; double alpha; int n;          // a = X + alpha*PQ is still pending (it lands in memory with the p,q update)
-    __device__ __forceinline__ double operator()(int row, double gw, double ru) const {
-        return (row < n) ? gw * ru : ((X[row] + alpha * PQ[row]) + ru) * gw;
+    struct Pre { double x, pq; };
+    __device__ __forceinline__ Pre pre(int row) const {
+        Pre P;
+        P.x = row >= n ? X[row] : 0.0;          // loads only, no branch around them
+        P.pq = row >= n ? PQ[row] : 0.0;
+        return P;
+    }
+    __device__ __forceinline__ double fin(int row, double gw, double ru, const Pre &P) const {
+        return (row < n) ? gw * ru : ((P.x + alpha * P.pq) + ru) * gw;
     }
 };
 
@@ -197,12 +204,19 @@ struct LanczosRider {
     double *VKP1;
     double alpha, beta;
     int n;
-    __device__ __forceinline__ double operator()(int row, double xi, double yi) const {
-        const double vk = VK[row];
+    struct Pre { double vk, vkm1; };
+    __device__ __forceinline__ Pre pre(int row) const {
+        Pre P;
+        P.vk = VK[row];
+        P.vkm1 = (VKM1 ? VKM1 : VK)[row];       // unused without VKM1
+        return P;
+    }
+    __device__ __forceinline__ double fin(int row, double xi, double yi, const Pre &P) const {
+        const double vk = P.vk;
         double v, u;
         if (row < n) { u = xi; v = yi - alpha * vk; }
         else { u = -xi; v = vk - yi; v = v - alpha * vk; }
-        if (VKM1) v = v - beta * VKM1[row];
+        if (VKM1) v = v - beta * P.vkm1;
         VKP1[row] = v;
         return u * v;
     }

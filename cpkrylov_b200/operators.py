@@ -219,6 +219,10 @@ class opLDL2:
         return L, d
 
     def close(self):
+        cached = getattr(self, "_system", None)
+        if cached is not None and not getattr(cached, "owns_M", True):
+            self._system = None
+            cached.close()              # the device copy of (A, C) a solver call cached on this operator
         if getattr(self, "handle", None) is not None and not self._owned_by_system:
             try:
                 _lib.lib().cpk_destroy(self.handle)
@@ -233,7 +237,10 @@ class opLDL2:
 class KktSystem:
     """Device-resident (A, C, M) of ``method(b1, A, C, M, opts)``."""
 
-    def __init__(self, A, Cm, M: opLDL2):
+    def __init__(self, A, Cm, M: opLDL2, owns_M=True):
+        """``owns_M``: closing the system also destroys M (the driver and the batch solver create
+        M themselves); a solver called as ``method(b1, A, C, M, opts)`` passes False -- M is the
+        caller's and outlives the system."""
         if not isinstance(M, opLDL2):
             raise TypeError("M must be a cpkrylov_b200.opLDL2 (GPU operator handle)")
         if not (sp.issparse(A) or isinstance(A, np.ndarray)):
@@ -247,6 +254,7 @@ class KktSystem:
         h = ct.c_uint64(0)
         _lib.check(_lib.lib().cpk_system_create(ct.byref(h), a.ref(), c.ref(), M.handle))
         self.handle = h
+        self.owns_M = bool(owns_M)
         M._owned_by_system = True
 
     def update(self, A, Cm):
@@ -268,7 +276,8 @@ class KktSystem:
             try:
                 _lib.lib().cpk_destroy(self.handle)
                 self.M._owned_by_system = False
-                self.M.close()
+                if self.owns_M:
+                    self.M.close()
             except Exception:
                 pass
             self.handle = None

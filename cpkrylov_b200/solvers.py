@@ -88,13 +88,31 @@ def _print_history(name, stats):
     print()
 
 
+def _content_key(X):
+    """Identity of a sparse matrix by CONTENT (shape, pattern and value checksums), cheap enough
+    to evaluate on every call: an `id()` would hit a stale device copy after an in-place change
+    of the values, or after the interpreter reuses the id of a collected temporary."""
+    X = X if sp.issparse(X) else sp.csc_matrix(X)
+    X = X.tocsc() if X.format not in ("csc", "csr") else X
+    return (X.format, X.shape, int(X.nnz), int(X.indptr[-1]), int(np.bitwise_xor.reduce(X.indices.astype(np.int64) * 2654435761 % (1 << 31))) if X.nnz else 0,
+            float(X.data.sum()), float(np.abs(X.data).sum()), float(X.data[::7].sum()))
+
+
 def _system_of(A, Cm, M):
+    """The device system (A, C, M) behind ``method(b1, A, C, M, opts)``.  One opLDL2 may be
+    used with any A, C (the reference passes M next to them, e.g. cpminres.m:1): the device copy
+    of (A, C) is cached on M by content and replaced -- without touching M -- when another
+    pair arrives."""
     if isinstance(A, KktSystem):
         return A
+    key = (_content_key(A), _content_key(Cm))
     sysobj = getattr(M, "_system", None)
-    if sysobj is None or sysobj._key != (id(A), id(Cm)):
-        sysobj = KktSystem(A, Cm, M)
-        sysobj._key = (id(A), id(Cm))
+    if sysobj is not None and (sysobj.handle is None or sysobj._key != key):
+        sysobj.close()                  # frees the device copy of the old (A, C); M stays (it is the caller's)
+        sysobj = None
+    if sysobj is None:
+        sysobj = KktSystem(A, Cm, M, owns_M=False)
+        sysobj._key = key
         M._system = sysobj
     return sysobj
 
@@ -192,7 +210,7 @@ def reg_cpkrylov(method, b, A, B, Cm, G, opts=None, factors=None, ldl_method="au
     B = sp.csc_matrix(B); Cm = sp.csc_matrix(Cm); G = sp.csc_matrix(G)
     n, m = A.shape[0], B.shape[0]
     M = opLDL2(G, B, -Cm, factors=factors, ldl_method=ldl_method, device=device, perm=perm)    # :131
-    S = KktSystem(A, Cm, M)
+    S = KktSystem(A, Cm, M, owns_M=True)
     ptime = time.perf_counter() - tstartp
     apply_opts_to_M(M, opts)
 

@@ -18,8 +18,11 @@
  *     argument, in which case CPK_MEM_DEVICE means "device pointer on the
  *     handle's GPU" (used to keep rhs/solution resident in HBM);
  *   - calls are synchronous (return after the handle's stream has drained);
- *     a handle must not be used from two host threads at once; different
- *     handles are independent.
+ *     the entry points that launch kernels serialise on one process-wide lock
+ *     (a solve owns every SM of its device), so the library may be called from
+ *     several host threads; a handle must still not be destroyed while another
+ *     thread uses it.
+ *   - `hist` buffers are always HOST pointers, whatever `mem` says.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point
  *     fails with CPK_ERR_CUDA.
  */

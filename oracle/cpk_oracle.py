@@ -51,6 +51,51 @@ import scipy.sparse as sp
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _EPS = float(np.finfo(np.float64).eps)
 
+# --------------------------------------------------------------------------
+# Working precision.  The restatement runs in IEEE fp64 like the reference.  As an ARBITER
+# for parity tests (which of two fp64 runs is closer to the exactly-rounded result of the same
+# algorithm?) every vector and scalar can instead be carried in the C `long double` of the host
+# (x87 80-bit on x86-64: 64-bit mantissa): ``with extended_precision(): ...``.  Matrices,
+# factors and thresholds (eps) stay fp64 data; only the arithmetic widens.
+# --------------------------------------------------------------------------
+_RT = np.float64
+
+
+class extended_precision:
+    def __enter__(self):
+        global _RT
+        self._old = _RT
+        _RT = np.longdouble
+        return self
+
+    def __exit__(self, *a):
+        global _RT
+        _RT = self._old
+
+
+def is_extended():
+    return _RT is np.longdouble
+
+
+def _f(v):
+    return _RT(v)
+
+
+def _zeros(shape, order="C"):
+    return np.zeros(shape, dtype=_RT, order=order)
+
+
+def _empty(shape):
+    return np.empty(shape, dtype=_RT)
+
+
+def _sqrt(v):
+    return math.sqrt(v) if _RT is np.float64 else np.sqrt(_RT(v))
+
+
+def _hypot(a, b):
+    return math.hypot(a, b) if _RT is np.float64 else np.hypot(_RT(a), _RT(b))
+
 
 # --------------------------------------------------------------------------
 # C kernels (oracle/kernels.c) with a SciPy/NumPy fallback of the same loops
@@ -96,14 +141,19 @@ class _Csr:
         self._sp = A
 
     def matvec(self, x):
-        x = np.ascontiguousarray(x, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=_RT)
         lib = _c()
         if not lib:
             return self._sp @ x
-        y = np.empty(self.shape[0])
-        lib.orc_csr_matvec(ctypes.c_int64(self.shape[0]), _p(self.rowptr, ctypes.c_int64),
-                           _p(self.col, ctypes.c_int64), _p(self.val, ctypes.c_double),
-                           _p(x, ctypes.c_double), _p(y, ctypes.c_double))
+        y = _empty(self.shape[0])
+        if _RT is np.float64:
+            lib.orc_csr_matvec(ctypes.c_int64(self.shape[0]), _p(self.rowptr, ctypes.c_int64),
+                               _p(self.col, ctypes.c_int64), _p(self.val, ctypes.c_double),
+                               _p(x, ctypes.c_double), _p(y, ctypes.c_double))
+        else:
+            lib.orc_csr_matvec_ld(ctypes.c_int64(self.shape[0]), _p(self.rowptr, ctypes.c_int64),
+                                  _p(self.col, ctypes.c_int64), _p(self.val, ctypes.c_double),
+                                  _p(x, ctypes.c_longdouble), _p(y, ctypes.c_longdouble))
         return y
 
 
@@ -138,21 +188,21 @@ def sym_givens(a, b):
         if a == 0:
             c = 1.0
         else:
-            c = float(_sign(a))
+            c = _f(_sign(a))
         s = 0.0
         d = abs(a)
     elif a == 0:
         c = 0.0
-        s = float(_sign(b))
+        s = _f(_sign(b))
         d = abs(b)
     elif abs(b) > abs(a):
         t = a / b
-        s = _sign(b) / math.sqrt(1 + t * t)
+        s = _sign(b) / _sqrt(1 + t * t)
         c = s * t
         d = b / s
     else:
         t = b / a
-        c = _sign(a) / math.sqrt(1 + t * t)
+        c = _sign(a) / _sqrt(1 + t * t)
         s = c * t
         d = a / c
     return c, s, d
@@ -198,8 +248,8 @@ class OpLDL2:
         self.force_itref = False
         self.residual_update = False
         self.ru_stateful = ru_stateful
-        self.Aty = np.zeros(nA)                                                 # opLDL2.m:90
-        self.Cy = np.zeros(nC)                                                  # opLDL2.m:91
+        self.Aty = _zeros(nA)                                                 # opLDL2.m:90
+        self.Cy = _zeros(nC)                                                  # opLDL2.m:91
         self.rNorm = None
         self.napply = 0
         self.nsolve = 0
@@ -207,25 +257,27 @@ class OpLDL2:
     # op.LDL = P * inv(L') * inv(D) * inv(L) * P'   (opLDL2.m:86), right to left
     def ldl_solve(self, x):
         self.nsolve += 1
-        w = np.ascontiguousarray(x[self.perm], dtype=np.float64)               # P' * x
+        w = np.ascontiguousarray(x[self.perm], dtype=_RT)               # P' * x
         lib = _c()
         Ls = self.Lstrict
         if lib:
             i64, f64 = ctypes.c_int64, ctypes.c_double
-            lib.orc_unit_lower_solve(i64(self.n), _p(Ls.rowptr, i64), _p(Ls.col, i64),
-                                     _p(Ls.val, f64), _p(w, f64))               # L \ .
-            lib.orc_block_diag_solve(i64(self.n), _p(self.d, f64), _p(self.e, f64),
-                                     _p(w, f64))                                # D \ .
-            lib.orc_unit_lower_transpose_solve(i64(self.n), _p(Ls.rowptr, i64), _p(Ls.col, i64),
-                                               _p(Ls.val, f64), _p(w, f64))     # L' \ .
+            ext = _RT is not np.float64
+            wt = ctypes.c_longdouble if ext else f64
+            fwd = lib.orc_unit_lower_solve_ld if ext else lib.orc_unit_lower_solve
+            dsl = lib.orc_block_diag_solve_ld if ext else lib.orc_block_diag_solve
+            bwd = lib.orc_unit_lower_transpose_solve_ld if ext else lib.orc_unit_lower_transpose_solve
+            fwd(i64(self.n), _p(Ls.rowptr, i64), _p(Ls.col, i64), _p(Ls.val, f64), _p(w, wt))    # L \ .
+            dsl(i64(self.n), _p(self.d, f64), _p(self.e, f64), _p(w, wt))                        # D \ .
+            bwd(i64(self.n), _p(Ls.rowptr, i64), _p(Ls.col, i64), _p(Ls.val, f64), _p(w, wt))    # L' \ .
         else:  # pragma: no cover - same loops in Python, small cases only
             w = _py_ldl(self.n, Ls, self.d, self.e, w)
-        y = np.empty(self.n)
+        y = _empty(self.n)
         y[self.perm] = w                                                        # P * .
         return y
 
     def __matmul__(self, x):
-        return self.multiply(np.asarray(x, dtype=np.float64))
+        return self.multiply(np.asarray(x, dtype=_RT))
 
     def multiply(self, x):
         """ops/opLDL2.m:161-188."""
@@ -242,21 +294,21 @@ class OpLDL2:
             self.Cy = self._K22.matvec(y[n:])
         if self.nitref > 0:                                                     # :174
             r = x - self.K.matvec(y)
-            rNorm = float(np.linalg.norm(r))
-            xNorm = float(np.linalg.norm(x))
+            rNorm = _f(np.linalg.norm(r))
+            xNorm = _f(np.linalg.norm(x))
             nit = 0
             while nit < self.nitref and (rNorm >= self.itref_tol * xNorm or self.force_itref):
                 dy = self.ldl_solve(r)
                 y = y + dy
                 r = x - self.K.matvec(y)
-                rNorm = float(np.linalg.norm(r))
+                rNorm = _f(np.linalg.norm(r))
                 nit += 1
             self.rNorm = rNorm
         return y
 
     def divide(self, b):
         """ops/opLDL2.m:193-195: M \\ b = K_P * b."""
-        return self.K.matvec(np.asarray(b, dtype=np.float64))
+        return self.K.matvec(np.asarray(b, dtype=_RT))
 
 
 def _py_ldl(n, Ls, d, e, w):  # pragma: no cover
@@ -294,7 +346,7 @@ class SolverError(RuntimeError):
     """error(...) / MException thrown inside a solver; ``identifier`` mirrors
     the MException id where the reference sets one."""
 
-    def __init__(self, msg, identifier="", iteration=0, value=float("nan")):
+    def __init__(self, msg, identifier="", iteration=0, value=_f("nan")):
         super().__init__(msg)
         self.identifier = identifier
         self.iteration = iteration
@@ -321,25 +373,25 @@ def cpcg(b, A, C, M, opts=None):
     rtol = _opt(opts, "rtol", 1.0e-6)
     itmax = _opt(opts, "itmax", n)
 
-    x = np.zeros(n)
-    a = np.zeros(m)
-    w = np.zeros(m)
-    g = -np.asarray(b, dtype=np.float64)
+    x = _zeros(n)
+    a = _zeros(m)
+    w = _zeros(m)
+    g = -np.asarray(b, dtype=_RT)
 
     ru = M @ np.concatenate([g, w]); r = ru[:n]; u = ru[n:]                     # :125
     p = -r
     q = -u
 
-    residNorm2 = float(g @ r)                                                   # :130
-    residNorm = math.sqrt(residNorm2) if residNorm2 >= 0 else float("nan")
+    residNorm2 = _f(g @ r)                                                   # :130
+    residNorm = _sqrt(residNorm2) if residNorm2 >= 0 else _f("nan")
     stopTol = atol + rtol * residNorm
     residHistory = [residNorm]
     itn = 0
 
     while residNorm > stopTol and itn < itmax:                                  # :147
         itn += 1
-        Ap = A @ p; pAp = float(p @ Ap)
-        Cq = C @ q; qCq = float(q @ Cq)
+        Ap = A @ p; pAp = _f(p @ Ap)
+        Cq = C @ q; qCq = _f(q @ Cq)
         alpha = residNorm2 / (pAp + qCq)
 
         x = x + alpha * p
@@ -349,14 +401,14 @@ def cpcg(b, A, C, M, opts=None):
 
         ru = M @ np.concatenate([g, w]); r = ru[:n]; u = ru[n:]                 # :166
         t = a + u
-        residNorm2_new = float(g @ r) + float(t @ w)
+        residNorm2_new = _f(g @ r) + _f(t @ w)
         beta = residNorm2_new / residNorm2
 
         p = -r + beta * p
         q = -t + beta * q
 
         residNorm2 = residNorm2_new
-        residNorm = math.sqrt(residNorm2) if residNorm2 >= 0 else float("nan")  # :175 (complex in MATLAB)
+        residNorm = _sqrt(residNorm2) if residNorm2 >= 0 else _f("nan")  # :175 (complex in MATLAB)
         residHistory.append(residNorm)
 
     flag = {"solved": bool(residNorm <= stopTol)}
@@ -368,16 +420,16 @@ def cpcg(b, A, C, M, opts=None):
 # shared Lanczos start (cpcglanczos.m:153-171, cpminres.m:131-148, cpsymmlq.m:137-154)
 # --------------------------------------------------------------------------
 def _lanczos_start(b, n, m, M, msg, ident=""):
-    u = np.asarray(b, dtype=np.float64)
-    t = np.zeros(m)
+    u = np.asarray(b, dtype=_RT)
+    t = _zeros(m)
     vprec = M @ np.concatenate([u, t])
     vkp1 = vprec[:n].copy()
     qkp1 = -vprec[n:]
-    beta = float(u @ vkp1)
+    beta = _f(u @ vkp1)
     eps100 = 100 * _EPS
     if beta < -eps100:
         raise _indef(0, beta, msg, ident=ident)
-    beta = math.sqrt(abs(beta))
+    beta = _sqrt(abs(beta))
     if beta > 0:
         vkp1 = vkp1 / beta
         qkp1 = qkp1 / beta
@@ -389,7 +441,7 @@ def _lanczos_step(A, C, M, n, vk, qk, vkm1, qkm1, beta, k, msg, ident="", second
     drops the beta*vkm1 term (cpsymmlq.m:202-204, second Lanczos vector)."""
     u = A @ vk
     t = C @ qk
-    alpha = float(u @ vk) + float(t @ qk)
+    alpha = _f(u @ vk) + _f(t @ qk)
     vprec = M @ np.concatenate([u, -t])
     if vkm1 is None:
         vkp1 = vprec[:n] - alpha * vk
@@ -399,10 +451,10 @@ def _lanczos_step(A, C, M, n, vk, qk, vkm1, qkm1, beta, k, msg, ident="", second
         vkp1 = vprec[:n] - alpha * vk - beta * vkm1
         qkp1 = qk - vprec[n:]
         qkp1 = qkp1 - alpha * qk - beta * qkm1
-    beta = float(u @ vkp1) + float(t @ qkp1)
+    beta = _f(u @ vkp1) + _f(t @ qkp1)
     if beta < -100 * _EPS:
         raise _indef(k, beta, msg, second=second, ident=ident)
-    beta = math.sqrt(abs(beta))
+    beta = _sqrt(abs(beta))
     if beta > 0:
         vkp1 = vkp1 / beta
         qkp1 = qkp1 / beta
@@ -421,10 +473,10 @@ def cpcglanczos(b, A, C, M, opts=None):
     itmax = _opt(opts, "itmax", n)
     ident = "CPCGLanczos:IndefiniteError"
 
-    x = np.zeros(n)
-    y = np.zeros(m)
-    vk = np.zeros(n)
-    qk = np.zeros(m)
+    x = _zeros(n)
+    y = _zeros(m)
+    vk = _zeros(n)
+    qk = _zeros(m)
     oldbeta = 0.0
     opNorm2 = 0.0
 
@@ -456,7 +508,7 @@ def cpcglanczos(b, A, C, M, opts=None):
         # the x/y update (:238-239) needs alpha only; keep statement order
         u = A @ vk
         t = C @ qk
-        alpha = float(u @ vk) + float(t @ qk)
+        alpha = _f(u @ vk) + _f(t @ qk)
         dg = alpha - low * low * dg
         zeta = eta / dg
         x = x + zeta * wv
@@ -466,10 +518,10 @@ def cpcglanczos(b, A, C, M, opts=None):
         vkp1 = vprec[:n] - alpha * vk - beta * vkm1
         qkp1 = qk - vprec[n:]
         qkp1 = qkp1 - alpha * qk - beta * qkm1
-        beta = float(u @ vkp1) + float(t @ qkp1)
+        beta = _f(u @ vkp1) + _f(t @ qkp1)
         if beta < -100 * _EPS:
             raise _indef(k, beta, _SOS_MSG, ident=ident)
-        beta = math.sqrt(abs(beta))
+        beta = _sqrt(abs(beta))
         if beta > 0:
             vkp1 = vkp1 / beta
             qkp1 = qkp1 / beta
@@ -480,18 +532,18 @@ def cpcglanczos(b, A, C, M, opts=None):
         wq = qkp1 - low * wq
 
         if btol > 0:                                                            # :271-291
-            rho = math.sqrt(rhobar * rhobar + low * low)
+            rho = _sqrt(rhobar * rhobar + low * low)
             cs = rhobar / rho
             sn = low / rho
             num = zeta - delta * tau
             taubar = num / rhobar
             tau = num / rho
-            xNorm = math.sqrt(xxNorm2 + taubar * taubar)
+            xNorm = _sqrt(xxNorm2 + taubar * taubar)
             xxNorm2 = xxNorm2 + tau * tau
             delta = sn
             rhobar = -cs
             opNorm2 = opNorm2 + alpha * alpha + beta * beta + oldbeta * oldbeta
-            opNorm = math.sqrt(opNorm2)
+            opNorm = _sqrt(opNorm2)
             bkerr = opNorm * xNorm + beta1
             bstopTol = btol * bkerr
 
@@ -522,16 +574,16 @@ def cpminres(b, A, C, M, opts=None):
     rtol = _opt(opts, "rtol", 1.0e-6)
     itmax = _opt(opts, "itmax", n)
 
-    x = np.zeros(n)
-    y = np.zeros(m)
-    vk = np.zeros(n)
-    qk = np.zeros(m)
+    x = _zeros(n)
+    y = _zeros(m)
+    vk = _zeros(n)
+    qk = _zeros(m)
 
     vkp1, qkp1, beta = _lanczos_start(b, n, m, M, _SPD_MSG)
     wv = vkp1
     wq = qkp1
-    wv2 = np.zeros(n)
-    wq2 = np.zeros(m)
+    wv2 = _zeros(n)
+    wq2 = _zeros(m)
     residNorm = beta
     residHistory = [residNorm]
 
@@ -557,7 +609,7 @@ def cpminres(b, A, C, M, opts=None):
         epsln = sn * beta
         deltabar = -cs * beta
 
-        gamma = math.hypot(gammabar, beta)                                      # norm([gammabar beta]) :218
+        gamma = _hypot(gammabar, beta)                                      # norm([gammabar beta]) :218
         cs = gammabar / gamma
         sn = beta / gamma
         tau = cs * taubar
@@ -587,12 +639,12 @@ def cpsymmlq(b, A, C, M, opts=None):
     atol = _opt(opts, "atol", 1.0e-6)
     rtol = _opt(opts, "rtol", 1.0e-6)
     itmax = _opt(opts, "itmax", n)
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b, dtype=_RT)
 
-    x = np.zeros(n)
-    y = np.zeros(m)
-    wv = np.zeros(n)
-    wq = np.zeros(m)
+    x = _zeros(n)
+    y = _zeros(m)
+    wv = _zeros(n)
+    wq = _zeros(m)
     k = 0
 
     vkp1, qkp1, beta1 = _lanczos_start(b, n, m, M, _SPD_MSG)
@@ -623,12 +675,12 @@ def cpsymmlq(b, A, C, M, opts=None):
         matnorm2 = alpha * alpha + beta * beta
 
         while cgresidNorm > stopTol and k < itmax:                              # :229
-            matnorm = math.sqrt(matnorm2)
+            matnorm = _sqrt(matnorm2)
             epsmat = matnorm * _EPS
             den = gammabar
             if den == 0:
                 den = epsmat
-            lqresidNorm = math.hypot(epsdelzeta, epsilonzeta)
+            lqresidNorm = _hypot(epsdelzeta, epsilonzeta)
             qrresidNorm = snprod * beta1
             cgresidNorm = qrresidNorm * beta / abs(den)
             lqresidHistory.append(lqresidNorm)
@@ -646,7 +698,7 @@ def cpsymmlq(b, A, C, M, opts=None):
 
             matnorm2 = matnorm2 + alpha * alpha + beta * beta + betaold * betaold
 
-            gamma = math.hypot(gammabar, betaold)                               # :291-297
+            gamma = _hypot(gammabar, betaold)                               # :291-297
             cs = gammabar / gamma
             sn = betaold / gamma
             delta = cs * deltabar + sn * alpha
@@ -667,12 +719,12 @@ def cpsymmlq(b, A, C, M, opts=None):
             epsdelzeta = epsilonzeta - delta * zeta
             epsilonzeta = -epsilon * zeta
 
-        matnorm = math.sqrt(matnorm2)                                           # :318-327
+        matnorm = _sqrt(matnorm2)                                           # :318-327
         epsmat = matnorm * _EPS
         den = gammabar
         if den == 0:
             den = epsmat
-        lqresidNorm = math.hypot(epsdelzeta, epsilonzeta)
+        lqresidNorm = _hypot(epsdelzeta, epsilonzeta)
         qrresidNorm = snprod * beta1
         lqresidHistory.append(lqresidNorm)
         qrresidHistory.append(qrresidNorm)
@@ -684,7 +736,7 @@ def cpsymmlq(b, A, C, M, opts=None):
             x = x + zetabar * wv
             y = y - zetabar * wq
 
-        vprec = M @ np.concatenate([b, np.zeros(m)])                            # :342-347
+        vprec = M @ np.concatenate([b, _zeros(m)])                            # :342-347
         vk = vprec[:n]
         qk = -vprec[n:]
         bstep = bstep / beta1
@@ -708,7 +760,7 @@ def _sqrt_real(v):
     # sqrt(real(v)), which is the same complex number, so the value kept is
     # purely imaginary.  A negative P-inner product is a breakdown; return NaN
     # so that the caller's tests fail the same way (NaN > stopTol is false).
-    return math.sqrt(v) if v >= 0 else float("nan")
+    return _sqrt(v) if v >= 0 else _f("nan")
 
 
 def cpgmres(b, A, C, M, opts=None):
@@ -718,32 +770,32 @@ def cpgmres(b, A, C, M, opts=None):
     rtol = _opt(opts, "rtol", 1.0e-6)
     restart = int(_opt(opts, "restart", 50))
     itmax = _opt(opts, "itmax", n + m)
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b, dtype=_RT)
 
-    g = np.zeros(restart + 1)
-    V = np.zeros((n, restart + 1), order="F")
-    Q = np.zeros((m, restart + 1), order="F")
-    H = np.zeros((restart + 1, restart))
-    c = np.zeros(restart)
-    s = np.zeros(restart)
+    g = _zeros(restart + 1)
+    V = _zeros((n, restart + 1), order="F")
+    Q = _zeros((m, restart + 1), order="F")
+    H = _zeros((restart + 1, restart))
+    c = _zeros(restart)
+    s = _zeros(restart)
 
-    x = np.zeros(n)
-    y = np.zeros(m)
+    x = _zeros(n)
+    y = _zeros(m)
 
     finished = False
     outer = 0
     outermax = int(math.ceil(itmax / restart))
     residHistory = []
-    residNorm = float("nan")
-    stopTol = float("nan")
+    residNorm = _f("nan")
+    stopTol = _f("nan")
     k = 0
 
     while (not finished) and outer < outermax:                                  # :155
         outer += 1
-        q = np.zeros(m)
+        q = _zeros(m)
         if outer == 1:
             u = b
-            t = np.zeros(m)
+            t = _zeros(m)
             w = M @ np.concatenate([u, -t])
             V[:, 0] = w[:n]
             Q[:, 0] = -w[n:]
@@ -753,7 +805,7 @@ def cpgmres(b, A, C, M, opts=None):
             w = M @ np.concatenate([u, -t])
             V[:, 0] = w[:n]
             Q[:, 0] = y - w[n:]
-        residNorm = _sqrt_real(float(u @ V[:, 0]) + float(t @ Q[:, 0]))         # :173
+        residNorm = _sqrt_real(_f(u @ V[:, 0]) + _f(t @ Q[:, 0]))         # :173
         if residNorm != 0:
             V[:, 0] = V[:, 0] / residNorm
             Q[:, 0] = Q[:, 0] / residNorm
@@ -772,10 +824,10 @@ def cpgmres(b, A, C, M, opts=None):
             V[:, k] = w[:n]
             Q[:, k] = Q[:, k - 1] - w[n:]
             for j in range(1, k + 1):
-                H[j - 1, k - 1] = float(V[:, j - 1] @ u) + float(Q[:, j - 1] @ t)
+                H[j - 1, k - 1] = _f(V[:, j - 1] @ u) + _f(Q[:, j - 1] @ t)
                 V[:, k] = V[:, k] - H[j - 1, k - 1] * V[:, j - 1]
                 Q[:, k] = Q[:, k] - H[j - 1, k - 1] * Q[:, j - 1]
-            H[k, k - 1] = _sqrt_real(float(u @ V[:, k]) + float(t @ Q[:, k]))   # :219
+            H[k, k - 1] = _sqrt_real(_f(u @ V[:, k]) + _f(t @ Q[:, k]))   # :219
             if H[k, k - 1] != 0:
                 V[:, k] = V[:, k] / H[k, k - 1]
                 Q[:, k] = Q[:, k] / H[k, k - 1]
@@ -793,7 +845,7 @@ def cpgmres(b, A, C, M, opts=None):
             residHistory.append(residNorm)
 
         # z = H(1:k,1:k) \ g(1:k): upper-triangular back substitution (:257)
-        z = np.zeros(k)
+        z = _zeros(k)
         for i in range(k - 1, -1, -1):
             acc = g[i]
             for j in range(i + 1, k):
@@ -822,38 +874,38 @@ def cpdqgmres(b, A, C, M, opts=None):
     mem = 50
     if opts is not None and "mem" in opts:
         mem = max(1, int(opts["mem"]))
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b, dtype=_RT)
 
     mem = max(1, min(mem, itmax))                                               # :125 (itmax=0 would give empty arrays)
-    g = np.zeros(mem + 1)
-    V = np.zeros((n, mem + 1), order="F")
-    Q = np.zeros((m, mem + 1), order="F")
-    PV = np.zeros((n, mem + 1), order="F")
-    PQ = np.zeros((m, mem + 1), order="F")
-    c = np.zeros(max(mem, 1))
-    s = np.zeros(max(mem, 1))
+    g = _zeros(mem + 1)
+    V = _zeros((n, mem + 1), order="F")
+    Q = _zeros((m, mem + 1), order="F")
+    PV = _zeros((n, mem + 1), order="F")
+    PQ = _zeros((m, mem + 1), order="F")
+    c = _zeros(max(mem, 1))
+    s = _zeros(max(mem, 1))
     # H(j, 2+k-j) band storage (cpdqgmres.m:133); rows grown on demand instead
     # of zeros(itmax, mem+2) -- same values, row index j is absolute.
     Hrows = {}
 
     def Hget(j, kk):
         row = Hrows.get(j)
-        return 0.0 if row is None else float(row[kk])
+        return 0.0 if row is None else _f(row[kk])
 
     def Hset(j, kk, v):
         if j not in Hrows:
-            Hrows[j] = np.zeros(mem + 3)
+            Hrows[j] = _zeros(mem + 3)
         Hrows[j][kk] = v
 
-    x = np.zeros(n)
-    y = np.zeros(m)
+    x = _zeros(n)
+    y = _zeros(m)
     u = b
-    t = np.zeros(m)
+    t = _zeros(m)
 
     w = M @ np.concatenate([u, t])                                              # :151
     V[:, 0] = w[:n]
     Q[:, 0] = -w[n:]
-    residNorm = _sqrt_real(float(u @ V[:, 0]))
+    residNorm = _sqrt_real(_f(u @ V[:, 0]))
     if residNorm != 0:
         V[:, 0] = V[:, 0] / residNorm
         Q[:, 0] = Q[:, 0] / residNorm
@@ -877,11 +929,11 @@ def cpdqgmres(b, A, C, M, opts=None):
         for j in range(max(1, k - mem + 1), k + 1):                             # :210-216
             jpos = (j - 1) % (mem + 1)
             kk = 2 + k - j
-            h = float(V[:, jpos] @ u) + float(Q[:, jpos] @ t)
+            h = _f(V[:, jpos] @ u) + _f(Q[:, jpos] @ t)
             Hset(j, kk, h)
             V[:, kp1pos] = V[:, kp1pos] - h * V[:, jpos]
             Q[:, kp1pos] = Q[:, kp1pos] - h * Q[:, jpos]
-        hk1 = _sqrt_real(float(u @ V[:, kp1pos]) + float(t @ Q[:, kp1pos]))     # :218
+        hk1 = _sqrt_real(_f(u @ V[:, kp1pos]) + _f(t @ Q[:, kp1pos]))     # :218
         Hset(k, 1, hk1)
         if hk1 != 0:
             V[:, kp1pos] = V[:, kp1pos] / hk1
@@ -947,7 +999,7 @@ def reg_cpkrylov(method, b, A, B, C, G, opts=None, factor=None, ru_stateful=Fals
         solver = method
     else:
         solver = SOLVERS[method]
-    b = np.asarray(b, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=_RT).ravel()
     Aop = as_operator(A)
     B = sp.csr_matrix(B)
     C = sp.csr_matrix(C)
@@ -975,7 +1027,7 @@ def reg_cpkrylov(method, b, A, B, C, G, opts=None, factor=None, ru_stateful=Fals
     shift = False
     if np.any(b[n:n + m]):                                                      # :154
         shift = True
-        xy0 = M @ np.concatenate([np.zeros(n), b[n:n + m]])
+        xy0 = M @ np.concatenate([_zeros(n), b[n:n + m]])
         BT = _Csr(B.T)
         b1 = b[:n] - Aop @ xy0[:n] - BT.matvec(xy0[n:])
     else:

@@ -80,3 +80,60 @@ void orc_block_diag_solve(int64_t n, const double *d, const double *e, double *w
         }
     }
 }
+
+/* ---------------------------------------------------------------------------
+ * Extended-precision twins (vectors and accumulation in `long double`; matrix and factor
+ * entries stay the fp64 data the fp64 run uses).  They serve the ARBITER of the parity tests
+ * (cpk_oracle.extended_precision): which of two fp64 runs is closer to the exactly-rounded
+ * result of the same algorithm.  Same loops, same order.
+ * ------------------------------------------------------------------------- */
+void orc_csr_matvec_ld(int64_t nrows, const int64_t *rowptr, const int64_t *col,
+                       const double *val, const long double *x, long double *y)
+{
+    for (int64_t i = 0; i < nrows; ++i) {
+        long double s = 0.0L;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            s += (long double)val[k] * x[col[k]];
+        y[i] = s;
+    }
+}
+
+void orc_unit_lower_solve_ld(int64_t n, const int64_t *rowptr, const int64_t *col,
+                             const double *val, long double *w)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        long double s = w[i];
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            s -= (long double)val[k] * w[col[k]];
+        w[i] = s;
+    }
+}
+
+void orc_unit_lower_transpose_solve_ld(int64_t n, const int64_t *rowptr,
+                                       const int64_t *col, const double *val,
+                                       long double *w)
+{
+    for (int64_t i = n - 1; i >= 0; --i) {
+        const long double wi = w[i];
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            w[col[k]] -= (long double)val[k] * wi;
+    }
+}
+
+void orc_block_diag_solve_ld(int64_t n, const double *d, const double *e, long double *w)
+{
+    int64_t i = 0;
+    while (i < n) {
+        if (i + 1 < n && e[i] != 0.0) {
+            const long double a = d[i], b = e[i], c = d[i + 1];
+            const long double det = a * c - b * b;
+            const long double w0 = w[i], w1 = w[i + 1];
+            w[i]     = (c * w0 - b * w1) / det;
+            w[i + 1] = (a * w1 - b * w0) / det;
+            i += 2;
+        } else {
+            w[i] = w[i] / (long double)d[i];
+            i += 1;
+        }
+    }
+}
