@@ -159,6 +159,74 @@ def peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def flush_l2(torch, buf):
+    """writes a buffer larger than the 126 MB L2 so that the next launch starts cold"""
+    buf.add_(1.0)
+    torch.cuda.synchronize()
+
+
+def roofline_parts(torch, L, S, M, s, info, peak, reps=12):
+    """Per-kernel evidence (north star: SpMV and preconditioner apply EACH against the HBM
+    roofline): every kernel is launched stand-alone through the C ABI on device-resident
+    vectors, the L2 flushed before each launch, CUDA-event time of the launch (the library's
+    own events on its stream), algorithmic bytes of SURVEY 8d."""
+    from cpkrylov_b200 import _lib
+    n, m = s["n"], s["m"]
+    N = n + m
+    spmv = lambda nnz, r, c: 12 * nnz + 4 * (r + 1) + 8 * c + 8 * r
+    nnz_KP = s["G"].nnz + 2 * s["B"].nnz + s["C"].nnz
+    B_H, B_KP = spmv(s["H"].nnz, n, n), spmv(nnz_KP, N, N)
+    B_ldl = 24 * info["nnz_L_off"] + 48 * N
+    x = torch.randn(N, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    junk = torch.zeros(48 * 1024 * 1024, dtype=torch.float64, device="cuda")     # 384 MB
+    saved = (M.nitref, M.force_itref)
+
+    def timed(call):
+        ts = []
+        for _ in range(reps):
+            flush_l2(torch, junk)
+            st = _lib.StatsStruct()
+            _lib.check(call(ct.byref(st)))
+            ts.append(st.t_solve_ms * 1e3)
+        return float(np.median(ts[2:]))
+
+    out = {}
+    def put(name, us, nbytes, what):
+        gbs = nbytes / us / 1e3
+        out[name] = {"us": us, "bytes": nbytes, "GBs": gbs, "frac": gbs / peak, "what": what}
+    put("spmv_H", timed(lambda st: L.cpk_system_matvec(S.handle, 0, x.data_ptr(), y.data_ptr(), 1, st)), B_H,
+        "H*v (cpk_system_matvec), 12 nnz + 4(r+1) + 8c + 8r")
+    put("spmv_KP", timed(lambda st: L.cpk_ldl2_matvec(M.handle, x.data_ptr(), y.data_ptr(), 1, st)), B_KP,
+        "K_P*v (cpk_ldl2_matvec: the product inside the refinement residual)")
+    M.nitref = 0
+    put("ldl_solve", timed(lambda st: L.cpk_ldl2_apply(M.handle, x.data_ptr(), y.data_ptr(), 1, st)), B_ldl,
+        "M*z with nitref = 0: P L^-T D^-1 L^-1 P' alone, 24 nnz_off(L) + 48 N")
+    M.nitref = 3; M.force_itref = False
+    put("apply_default", timed(lambda st: L.cpk_ldl2_apply(M.handle, x.data_ptr(), y.data_ptr(), 1, st)), B_ldl + B_KP + 8 * N,
+        "M*z with the reference defaults (nitref = 3, no step taken): solve + residual pass")
+    M.nitref = 1; M.force_itref = True
+    put("apply_forced1", timed(lambda st: L.cpk_ldl2_apply(M.handle, x.data_ptr(), y.data_ptr(), 1, st)), 2 * B_ldl + B_KP + 8 * N + 24 * N,
+        "M*z with nitref = 1, force_itref (example options): 2 solves + 1 residual pass")
+    M.nitref, M.force_itref = saved
+    del junk
+    return out
+
+
+def parity_section(s, solver, opts, fac, x_gpu, stats_gpu):
+    """Untimed: the CPU restatement run to completion on the same system with the same factors;
+    backs the 'GPU = CPU restatement' columns of BASELINE.md with the driver's own run."""
+    from oracle import cpk_oracle as orc
+    orc.build_c_kernels()
+    t = time.perf_counter()
+    xo, so, fo = orc.reg_cpkrylov(solver, s["rhs"], s["H"], s["B"], s["C"], s["G"], dict(opts, print=False), factor=lambda K: fac)
+    ho = np.asarray(so.get("residHistory", so.get("cgresidHistory")), dtype=float)
+    return {"niters_oracle": int(so["niters"]), "niters_gpu": int(stats_gpu["niters"]), "solved_oracle": bool(fo["solved"]),
+            "solved_gpu": bool(stats_gpu["solved"]),
+            "relerr_vs_oracle": float(np.linalg.norm(x_gpu - xo) / np.linalg.norm(xo)), "oracle_s": time.perf_counter() - t,
+            "oracle_final_resid": float(ho[-1]), "note": "oracle = oracle/cpk_oracle.py, same (L, D, p); see tests/test_gpu_parity_full.py for the arbitrated bar"}
+
+
 def run_reference(args, rank, world):
     """CPU restatement of the reference on the host cores (rank 0 only)."""
     if rank != 0:
@@ -208,7 +276,8 @@ def run_batch(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lo, hi = partition(args.batch, world, rank)
+    total = args.batch_per_gpu * world if args.batch_per_gpu > 0 else args.batch
+    lo, hi = partition(total, world, rank)
     opts = dict(atol=1e-6, rtol=1e-6, itmax=500, residual_update=True, nitref=1, force_itref=True)
     t0 = time.perf_counter()
     if args.g > 0:
@@ -254,8 +323,8 @@ def run_batch(args, rank, local_rank, world):
         print(json.dumps({
             "metric": "krylov_iterations_per_second", "value": cnt.item() / wall_max, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ipm_batch", "g": args.g, "systems": args.batch, "n": base["n"], "m": base["m"], "solver": "cpminres",
+            "higher_is_better": True, "scaling": "weak" if args.batch_per_gpu > 0 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ipm_batch", "g": args.g, "systems": total, "n": base["n"], "m": base["m"], "solver": "cpminres",
                        "opts": opts, "systems_per_rank": hi - lo, "device_ms_per_step": dev_max / args.steps,
                        "setup_s": t_setup, "note": "end to end through the host-pointer batch ABI (H2D rhs, D2H solutions inside the timed region)"},
             "e2e": {"value": cnt.item() / wall_max, "unit": "iterations/s",
@@ -284,6 +353,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="collect per-phase cycle shares (slower)")
     ap.add_argument("--batch", type=int, default=256, help="systems in the ipm_batch workload")
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="ipm_batch: systems PER GPU (weak scaling) instead of --batch in total")
+    ap.add_argument("--no-parts", action="store_true", help="skip the stand-alone per-kernel roofline section")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -449,6 +521,10 @@ def main():
                          "kernel_ms": kernel_ms},
             "clocks": clocks,
         }
+        if not args.no_parts:
+            line["roofline_parts"] = roofline_parts(torch, L, S, M, s, info, peak)
+        if not args.no_parity:
+            line["parity"] = parity_section(s, solver, opts, M.factors, x_gpu, stats_last)
         if args.profile:
             tot = phase.sum() or 1.0
             line["phase_share"] = {nm: float(phase[i] / tot) for i, nm in enumerate(_lib.PHASE_NAMES)}

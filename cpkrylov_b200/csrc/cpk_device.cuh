@@ -48,6 +48,15 @@ struct DevSell {
     const int    *lptr;     // [nlong+1]
     const int    *lcol;
     const double *lval;
+    // Packed form of the padded entries (nullptr: not packed, col / val above are used; otherwise
+    // col / val are NOT uploaded): one 32-bit word per entry,
+    //     bits 0-15   column - row, signed (banded matrices: |column - row| < 32768)
+    //     bits 16-31  index into `dict`, the table of the matrix' distinct values (< 65536 of them)
+    // 4 bytes per entry instead of 12: lossless, chosen at upload when the matrix allows it
+    // (stencil matrices such as the H of the BASELINE configs: 2 resp. 7 distinct values).
+    const unsigned *pk;
+    const double   *dict;
+    int ndict;
 };
 
 // ---------------------------------------------------------------------------
@@ -63,26 +72,52 @@ struct DevSell {
 // 20 bytes of per-lane item metadata.  Rows with more than `maxw` entries form a CSR list of
 // their own (one warp per row).
 // A level is a run of pieces (one per class present).  Its batches (a few consecutive groups of
-// one piece) are dealt round robin to the warps of the team, computed on the fly from the piece
-// table -- no per-team split arrays: such a pass is bound by dependent round trips per warp, so
-// the warps must walk equal numbers of batches, not equal numbers of bytes.
+// one piece) form one sequence, cut into contiguous ranges of equal COST for the warps of the team
+// from the prefix sums in the piece table -- no per-team split arrays.  Such a pass is bound by
+// dependent round trips per warp, so the cost of a batch is its number of round trips, not bytes.
+// A warp's consecutive batches mostly lie in one piece, so the streamed loads of the next batch
+// are issued while the gathers of the current one are in flight.
 // ---------------------------------------------------------------------------
-struct RcPiece { int width, ngroups, row_off, ent_off; };   // width < 0: long rows (one row per group, ent_off = first row in lptr)
-constexpr int kRcInline = 40;       // pieces kept inside the descriptor (shared-memory copy); the rest is read from global memory
+struct RcPiece { int wn, cum, row_off, ent_off; };  // wn = width | ngroups << 8; cum = cost of the level's batches before this piece
+constexpr int kRcLongW = 255;       // width code of the long-row list (one row per "group", ent_off = first row in lptr)
+constexpr int kRcInline = 48;       // pieces kept inside the descriptor (shared-memory copy); the rest is read from global memory
 constexpr int kRcMaxLev = 48;
 constexpr int RC_IDX_BITS = 28;     // row / column codes: index in the low 28 bits
 constexpr int RC_IDX_MASK = (1 << RC_IDX_BITS) - 1;
-// column codes of a sweep: source of the gathered value in bits 28-29
-constexpr int RC_SRC_Y = 0, RC_SRC_W = 1, RC_SRC_IN = 2;
-// row codes of a sweep: flags in bits 28-29 (-1 = padding lane)
+// column codes of a sweep: bit 28 set = element of the INPUT vector; otherwise an index into the
+// sweep's value buffer [w (N) | y (N)], both halves indexed by the user index of a row
+constexpr int RC_SRC_IN = 1;
+// row codes of a sweep: user index + flags in bits 28-29 (-1 = padding lane)
 constexpr int RC_F_FUSED = 1;       // forward row whose column of L is empty: y = w/d, written to the output
 constexpr int RC_F_WDIRECT = 1;     // backward row without forward work: w = (P'z)_i read from the input
-constexpr int RC_F_STOREY = 2;      // y_i is gathered by a later level: keep it in yv
+constexpr int RC_F_STOREY = 2;      // y_i is gathered by a later level: keep it in the value buffer
+// groups of 32 rows per batch for the widths 0, 1, 2, 3 (one digit each, powers of two; wider rows: 1).
+// Host (batch prefix sums of the piece table) and device must agree, hence one table for all passes.
+#ifndef CPK_RC_B
+#define CPK_RC_B 4221
+#endif
+__host__ __device__ constexpr int rc_batch_of(int width)
+{
+    return width == 0 ? CPK_RC_B / 1000 % 10 : width == 1 ? CPK_RC_B / 100 % 10 : width == 2 ? CPK_RC_B / 10 % 10 : width == 3 ? CPK_RC_B % 10 : 1;
+}
+static_assert(((CPK_RC_B / 1000 % 10) | (CPK_RC_B / 100 % 10) | (CPK_RC_B / 10 % 10) | (CPK_RC_B % 10)) <= 7, "CPK_RC_B digits: 1, 2 or 4");
+// entries per lane a wide row (more than 3 entries) has in flight at a time
+#ifndef CPK_RC_CH
+#define CPK_RC_CH 4
+#endif
+// Cost of one batch in dependent round trips, the unit the warps' shares of a level are measured
+// in: a batch of short rows is one round trip once the pipeline of its piece runs, a group of wide
+// rows one per chunk of CPK_RC_CH entries plus the row codes, a long row three.
+__host__ __device__ constexpr int rc_cost_of(int width)
+{
+    return width <= 3 ? 1 : width == kRcLongW ? 3 : 1 + (width + CPK_RC_CH - 1) / CPK_RC_CH;
+}
 
 struct DevRc {
     int nlev, npieces;
     int nfwd_lev;                   // sweeps: levels [0, nfwd_lev) are forward levels, the rest backward
     short levp[kRcMaxLev + 2];      // [nlev+1] first piece of every level
+    int   levb[kRcMaxLev + 1];      // [nlev] cost of every level (sum of rc_cost_of over its batches)
     RcPiece inl[kRcInline];
     const RcPiece *pieces;          // [npieces]
     const int    *rowmap;           // row code per position
@@ -204,8 +239,11 @@ struct DevLdl {
     // indexed by the USER index of a row, not by its LDL row id)
     int    use_rc;          // 1: walk `rc` instead of the item list
     DevRc  rc;
-    // K_P = [A B'; B C] for the refinement residual and `divide` (row-class layout, one level)
-    DevRc  KP;
+    // K_P = [A B'; B C] for the refinement residual and `divide`: SELL (streamed like H) or, when
+    // resid_rc is set, row-class layout (one level); only the chosen form is built
+    int     resid_rc;
+    DevSell KPs;
+    DevRc   KP;
     DevSell K12, K22;       // B' (nA x nC) and C (nC x nC) for the stateful residual update
     double *atycy;          // [N] = [Aty; Cy]
     double *rvec;           // [N] refinement residual

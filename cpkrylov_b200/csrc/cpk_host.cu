@@ -129,10 +129,45 @@ static std::vector<int> warp_split(const std::vector<int> &sptr, int nslices, in
 
 static int g_grid_warps_hint = 148 * kWarpsPerCta;
 
-static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d)
+// Packed entries of a SELL matrix (DevSell::pk): false when a column offset or the number of
+// distinct values does not fit.  Values are compared bit for bit (-0.0 and 0.0 are two values).
+static bool sell_pack(const HSell &h, std::vector<unsigned> &pk, std::vector<double> &dict)
+{
+    if (getenv("CPK_SELL_PACK") && atoi(getenv("CPK_SELL_PACK")) == 0) return false;
+    std::unordered_map<uint64_t, unsigned> index;
+    pk.assign(h.col.size(), 0u);
+    dict.clear();
+    for (int sl = 0; sl < h.nslices; ++sl) {
+        const int b = h.sptr[sl], en = h.sptr[sl + 1];
+        for (int k = b; k < en; ++k) {
+            const int lane = (k - b) & 31;
+            const int row = std::max(h.rowmap[(size_t)sl * 32 + lane], 0);      // idle lanes: entries (col 0, val 0) read x[0]
+            const int delta = h.col[k] - row;
+            if (delta < -32768 || delta > 32767) return false;
+            uint64_t bits;
+            memcpy(&bits, &h.val[k], 8);
+            auto it = index.find(bits);
+            unsigned id;
+            if (it == index.end()) {
+                if (dict.size() >= 256) return false;       // beyond a few values the table stops living in L1
+                id = (unsigned)dict.size();
+                index.emplace(bits, id);
+                dict.push_back(h.val[k]);
+            } else id = it->second;
+            pk[k] = ((unsigned)delta & 0xffffu) | (id << 16);
+        }
+    }
+    return true;
+}
+
+static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d, bool try_pack = false)
 {
     cudaError_t e;
     d.nrows = h.nrows; d.ncols = h.ncols; d.nslices = h.nslices;
+    d.pk = nullptr; d.dict = nullptr; d.ndict = 0;
+    std::vector<unsigned> pk;
+    std::vector<double> dict;
+    const bool packed = try_pack && sell_pack(h, pk, dict);
     {
         const int nw[2] = {g_grid_warps_hint, kWarpsPerCta};
         for (int kdx = 0; kdx < 2; ++kdx) {
@@ -142,8 +177,18 @@ static cudaError_t upload_sell(DevArena &ar, const HSell &h, DevSell &d)
         }
     }
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
-    if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
-    if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    if (packed) {
+        d.col = nullptr; d.val = nullptr;
+        if ((e = ar.upload(&d.pk, pk)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.dict, dict)) != cudaSuccess) return e;
+        d.ndict = (int)dict.size();
+        if (getenv("CPK_VERBOSE"))
+            fprintf(stderr, "[cpk] SELL matrix %d x %d packed: %zu entries, %zu distinct values, 4 instead of 12 bytes per entry\n",
+                    h.nrows, h.ncols, pk.size(), dict.size());
+    } else {
+        if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    }
     if ((e = ar.upload(&d.rowmap, h.rowmap)) != cudaSuccess) return e;
     d.nlong = (int)h.lrow.size();
     if ((e = ar.upload(&d.lrow, h.lrow)) != cudaSuccess) return e;
@@ -485,7 +530,7 @@ k_matvec_rc(const __grid_constant__ DevRc A, const double *x, double *y)
         for (int i = threadIdx.x; i < (int)(sizeof(DevRc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    MatvecOp op{{}, x, y};
+    MatvecOp op{x, y};
     if (GRID) {
         GridTeam T; T.init(nullptr, nullptr, nullptr);
         rc_level(s_A, 0, T.gwarp, T.nwarps, T.lane, op);
@@ -903,11 +948,12 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         return er;
     };
     // Which form(s) of the sweeps to build.  Shallow sweeps without 2x2 pivots are walked in
-    // row-class form (one pass per level); the item list is only built when a walk that needs
-    // it can be chosen: the sync-free walk (deep sweeps on a grid team, or forced through
-    // CPK_LDL_SYNCFREE), 2x2 pivots, CPK_LDL_RC=0.
+    // row-class form (one pass per level) when CPK_LDL_RC=1 asks for it; the item list is then only
+    // built when a walk that needs it can still be chosen: the sync-free walk (deep sweeps on a grid
+    // team, or forced through CPK_LDL_SYNCFREE), 2x2 pivots.  Default: the item list (measured
+    // 5-8 % faster inside the solver loop on cfg 3, profiles/r2_notes.md).
     const char *rcenv = getenv("CPK_LDL_RC");
-    const bool rc_ok = n2 == 0 && N < (1 << RC_IDX_BITS) && W.lev_f_eff + W.lev_b_eff <= kRcMaxLev && !(rcenv && atoi(rcenv) == 0);
+    const bool rc_ok = n2 == 0 && N < (1 << (RC_IDX_BITS - 1)) && W.lev_f_eff + W.lev_b_eff <= kRcMaxLev && rcenv && atoi(rcenv) == 1;
     const bool walk_deep = W.lev_f_eff + W.lev_b_eff > 24;
     const bool want_items = !rc_ok || walk_deep || getenv("CPK_LDL_SYNCFREE") != nullptr || getenv("CPK_LDL_ITEMS") != nullptr;
     bool have_rc = false;
@@ -932,7 +978,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         const int nlf_eff = std::max(W.lev_f_eff, 1);
         rc_append(RC, std::move(in), nlf_eff, [&](int r) {
             EncRow er = lone[r] ? EncRow() : entriesF(r);
-            for (auto &x : er) x.first = x.first >= 0 ? ((RC_SRC_W << RC_IDX_BITS) | (int)p[x.first]) : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2));
+            for (auto &x : er) x.first = x.first >= 0 ? (int)p[x.first] : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2));       // w_j | input
             return er;
         }, kRcSweepMaxW);
         RC.nfwd_lev = RC.nlev;
@@ -945,8 +991,8 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         rc_append(RC, std::move(inb), W.lev_b_eff, [&](int r) {
             EncRow er = entriesB(r);
             for (auto &x : er)
-                x.first = x.first >= N ? ((RC_SRC_W << RC_IDX_BITS) | (int)p[x.first - N])
-                        : (x.first >= 0 ? ((RC_SRC_Y << RC_IDX_BITS) | (int)p[x.first]) : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2)));
+                x.first = x.first >= N ? (int)p[x.first - N]                                                   // w_r
+                        : (x.first >= 0 ? N + (int)p[x.first] : ((RC_SRC_IN << RC_IDX_BITS) | (-x.first - 2)));       // y_r | input
             return er;
         }, kRcSweepMaxW);
         have_rc = rc_fits(RC);
@@ -1017,8 +1063,17 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, (int)nA, (int)nC);
     HSell sK12 = build_sell(Bt), sK22 = build_sell(Cr);
-    HRc rKP = build_rc(KP, kRcMatMaxW);
-    if (!rc_fits(rKP)) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
+    // K_P itself in ONE of two forms (CPK_RESID_RC=1: row-class passes; default: SELL, streamed like H)
+    const bool resid_rc = [] { const char *e = getenv("CPK_RESID_RC"); return e && atoi(e) == 1; }();
+    HRc rKP;
+    HSell sKP;
+    if (resid_rc) {
+        rKP = build_rc(KP, kRcMatMaxW);
+        if (!rc_fits(rKP)) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
+    } else {
+        sKP = build_sell(KP);
+        if ((int64_t)sKP.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "K_P exceeds int32 indexing");
+    }
 
     const double t_sell = ms_since(t_begin);
     // ---- upload
@@ -1035,8 +1090,8 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     CUDA_TRY(o->ar.alloc(&m.wbuf, N, true));        // tag 0 = never produced; epochs start at 1
     CUDA_TRY(o->ar.alloc(&m.ybuf, N, true));
     CUDA_TRY(o->ar.alloc(&m.epoch, 1, true));
-    CUDA_TRY(o->ar.alloc(&m.wv, N, true));
-    CUDA_TRY(o->ar.alloc(&m.yv, N, true));
+    CUDA_TRY(o->ar.alloc(&m.wv, 2 * (size_t)N, true));     // [w | y]: one buffer (the row-class passes address both halves through one base)
+    m.yv = m.wv + N;
     // walk selection: one barrier per level is cheapest for shallow sweeps (and keeps the
     // one-CTA team free of polling); a grid team facing a deep sweep uses the sync-free walk
     // (measured on the k=6 windowed stress system, 278+261 levels: 29 ms vs 54 ms per solve)
@@ -1065,8 +1120,10 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
             m.cw.nblk = cws.nblk;
         }
     }
-    CUDA_TRY(upload_rc(o->ar, rKP, m.KP));
-    o->kp_nval = (int64_t)rKP.val.size(); o->kp_nlval = (int64_t)rKP.lval.size();
+    m.resid_rc = resid_rc ? 1 : 0;
+    memset(&m.KP, 0, sizeof m.KP); memset(&m.KPs, 0, sizeof m.KPs);
+    if (resid_rc) CUDA_TRY(upload_rc(o->ar, rKP, m.KP)); else CUDA_TRY(upload_sell(o->ar, sKP, m.KPs));
+    o->kp_nval = (int64_t)(resid_rc ? rKP.val.size() : sKP.val.size()); o->kp_nlval = (int64_t)(resid_rc ? rKP.lval.size() : sKP.lval.size());
     o->patA = pattern_hash(A); o->patB = pattern_hash(B); o->patC = pattern_hash(C);
     CUDA_TRY(upload_sell(o->ar, sK12, m.K12));
     CUDA_TRY(upload_sell(o->ar, sK22, m.K22));
@@ -1090,7 +1147,8 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
                 want_items ? "built too" : "not built");
         for (int l = 0; l < RC.nlev; ++l)
             for (int q = RC.levp[l]; q < RC.levp[l + 1]; ++q)
-                fprintf(stderr, "[cpk]   level %d %s: width %d, %d groups\n", l, l < RC.nfwd_lev ? "fwd" : "bwd", RC.pieces[q].width, RC.pieces[q].ngroups);
+                fprintf(stderr, "[cpk]   level %d %s: width %d, %d groups, first batch %d of %d\n", l, l < RC.nfwd_lev ? "fwd" : "bwd",
+                        RC.pieces[q].wn & 255, RC.pieces[q].wn >> 8, RC.pieces[q].cum, RC.levb[l]);
     }
     if (getenv("CPK_VERBOSE"))
         fprintf(stderr, "[cpk] set-up ms: parse+levels %.2f, sweeps %.2f, K_P SELL %.2f, uploads+stream %.2f\n",
@@ -1144,7 +1202,7 @@ extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int
 //   sizes = {have_rc, nlev, nfwd_lev, npieces, len(rowmap), len(col), len(lptr), len(lcol)}
 // Call with the arrays NULL to get the sizes.
 extern "C" int cpk_debug_rc(const cpk_csc *A, const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int64_t *sizes,
-                            int *pieces, int *levp, int *rowmap, double *d, int *col, double *val, int *lptr, int *lcol, double *lval)
+                            int *pieces, int *levp, int *levb, int *rowmap, double *d, int *col, double *val, int *lptr, int *lcol, double *lval)
 {
     if (!sizes) return fail(CPK_ERR_ARG, "cpk_debug_rc: bad argument");
     return guarded([&] {
@@ -1171,6 +1229,7 @@ extern "C" int cpk_debug_rc(const cpk_csc *A, const cpk_csc *L, const cpk_csc *D
         sizes[5] = (int64_t)R->col.size(); sizes[6] = (int64_t)R->lptr.size(); sizes[7] = (int64_t)R->lcol.size();
         if (pieces) memcpy(pieces, R->pieces.data(), sizeof(RcPiece) * R->pieces.size());
         if (levp) std::copy(R->levp.begin(), R->levp.end(), levp);
+        if (levb) std::copy(R->levb.begin(), R->levb.end(), levb);
         if (rowmap) std::copy(R->rowmap.begin(), R->rowmap.end(), rowmap);
         if (d && R->with_d) std::copy(R->d.begin(), R->d.end(), d);
         if (col) std::copy(R->col.begin(), R->col.end(), col);
@@ -1350,13 +1409,20 @@ static int cpk_ldl2_refactor_impl(cpk_handle h, const cpk_csc *A, const cpk_csc 
     const int nA = M->d.nA, nC = M->d.nC;
     HCsr Ar = csr_from_csc(*A), Br = csr_from_csc(*B), Bt = csr_of_transpose(*B), Cr = csr_from_csc(*C);
     HCsr KP = block2x2(&Ar, &Bt, &Br, &Cr, nA, nC);
-    {
+    if (M->d.resid_rc) {
         const HRc rk = build_rc(KP, kRcMatMaxW);
         if ((int)rk.pieces.size() != M->d.KP.npieces || (int64_t)rk.val.size() != M->kp_nval || (int64_t)rk.lval.size() != M->kp_nlval)
             return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
         if (!rk.val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KP.val), rk.val.data(), sizeof(double) * rk.val.size(), cudaMemcpyHostToDevice, dc->stream));
         if (!rk.lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KP.lval), rk.lval.data(), sizeof(double) * rk.lval.size(), cudaMemcpyHostToDevice, dc->stream));
         CUDA_TRY(cudaStreamSynchronize(dc->stream));      // rk goes out of scope
+    } else {
+        const HSell sk = build_sell(KP);
+        if (sk.nslices != M->d.KPs.nslices || (int64_t)sk.val.size() != M->kp_nval || (int64_t)sk.lval.size() != M->kp_nlval)
+            return fail(CPK_ERR_DIM, "refactorization needs the sparsity pattern the operator was created with");
+        if (!sk.val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KPs.val), sk.val.data(), sizeof(double) * sk.val.size(), cudaMemcpyHostToDevice, dc->stream));
+        if (!sk.lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(M->d.KPs.lval), sk.lval.data(), sizeof(double) * sk.lval.size(), cudaMemcpyHostToDevice, dc->stream));
+        CUDA_TRY(cudaStreamSynchronize(dc->stream));
     }
     const HSell hs[2] = {build_sell(Bt), build_sell(Cr)};
     const DevSell *ds[2] = {&M->d.K12, &M->d.K22};
@@ -1412,6 +1478,19 @@ static int cpk_system_update_impl(cpk_handle h, const cpk_csc *A, const cpk_csc 
     for (int q = 0; q < 2; ++q) {
         if (hs[q]->nslices != ds[q]->nslices || (int)hs[q]->lrow.size() != ds[q]->nlong)
             return fail(CPK_ERR_DIM, "cpk_system_update needs the sparsity pattern the system was created with");
+        if (ds[q]->pk) {
+            // packed entries: the new values must still fit the value table
+            std::vector<unsigned> pk;
+            std::vector<double> dict;
+            if (!sell_pack(*hs[q], pk, dict) || (int)dict.size() > ds[q]->ndict)
+                return fail(CPK_ERR_UNSUPPORTED, "cpk_system_update: the system was created with packed matrix entries (few distinct values) and the "
+                                                 "new values do not fit its value table; create the system with CPK_SELL_PACK=0");
+            CUDA_TRY(cudaMemcpyAsync(const_cast<unsigned *>(ds[q]->pk), pk.data(), sizeof(unsigned) * pk.size(), cudaMemcpyHostToDevice, dc->stream));
+            CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->dict), dict.data(), sizeof(double) * dict.size(), cudaMemcpyHostToDevice, dc->stream));
+            if (!hs[q]->lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->lval), hs[q]->lval.data(), sizeof(double) * hs[q]->lval.size(), cudaMemcpyHostToDevice, dc->stream));
+            CUDA_TRY(cudaStreamSynchronize(dc->stream));      // pk / dict go out of scope
+            continue;
+        }
         if (!hs[q]->val.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->val), hs[q]->val.data(), sizeof(double) * hs[q]->val.size(), cudaMemcpyHostToDevice, dc->stream));
         if (!hs[q]->lval.empty()) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(ds[q]->lval), hs[q]->lval.data(), sizeof(double) * hs[q]->lval.size(), cudaMemcpyHostToDevice, dc->stream));
     }
@@ -1646,6 +1725,7 @@ int cpk_ldl2_matvec(cpk_handle h, const double *b, double *y, cpk_mem mem, cpk_s
 {
     Ldl2 *M = lookup<Ldl2>(h, OBJ_LDL2);
     if (!M || !b || !y) return fail(CPK_ERR_ARG, "cpk_ldl2_matvec: bad handle or null vector");
+    if (!M->d.resid_rc) return run_matvec(M->device, M->d.KPs, b, y, mem, stats, M->d_z, M->d_y);
     return run_matvec_rc(M->device, M->d.KP, M->d.N, b, y, mem, stats, M->d_z, M->d_y);
 }
 
@@ -1680,7 +1760,7 @@ static int cpk_system_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_c
     o->M = M; o->M_handle = Mh;
     DevSystem &d = o->h;
     d.n = n; d.m = m; d.N = n + m;
-    CUDA_TRY(upload_sell(o->ar, s, d.HC));
+    CUDA_TRY(upload_sell(o->ar, s, d.HC, true));           // packed entries when H, C allow it (stencil matrices)
     d.Hn = d.HC; d.Hn.nrows = n; d.Hn.ncols = n; d.Hn.nslices = h_slices; d.Hn.nlong = h_long;
     {
         const int nw[2] = {g_grid_warps_hint, kWarpsPerCta};

@@ -12,6 +12,7 @@ struct HRc {
     int nlev = 0, nfwd_lev = 0;
     std::vector<RcPiece> pieces;
     std::vector<int> levp;                  // [nlev+1]
+    std::vector<int> levb;                  // [nlev] batches per level
     std::vector<int> rowmap, col;
     std::vector<double> d, val;
     std::vector<int> lptr, lcol;
@@ -50,6 +51,7 @@ static void rc_append(HRc &R, std::vector<RcRowIn> rows, int nlevels, Entries en
     });
     size_t i0 = 0;
     for (int lev = 0; lev < nlevels; ++lev) {
+        int cum = 0;
         while (i0 < rows.size() && rows[i0].level == lev) {
             const int c = cls(rows[i0]);
             size_t i1 = i0;
@@ -58,7 +60,8 @@ static void rc_append(HRc &R, std::vector<RcRowIn> rows, int nlevels, Entries en
             RcPiece pc;
             if (c < (1 << 30)) {
                 const int ng = (cnt + 31) / 32, stride = ng * 32;
-                pc.width = c; pc.ngroups = ng; pc.row_off = (int)R.rowmap.size(); pc.ent_off = (int)R.col.size();
+                pc.wn = c | (ng << 8); pc.cum = cum; pc.row_off = (int)R.rowmap.size(); pc.ent_off = (int)R.col.size();
+                cum += (ng + rc_batch_of(c) - 1) / rc_batch_of(c) * rc_cost_of(c);
                 R.rowmap.resize(R.rowmap.size() + stride, -1);
                 if (R.with_d) R.d.resize(R.rowmap.size(), 1.0);
                 R.col.resize(R.col.size() + (size_t)c * stride, 0);
@@ -75,7 +78,8 @@ static void rc_append(HRc &R, std::vector<RcRowIn> rows, int nlevels, Entries en
                     }
                 }
             } else {
-                pc.width = -1; pc.ngroups = cnt; pc.row_off = (int)R.rowmap.size(); pc.ent_off = (int)R.lptr.size() - 1;
+                pc.wn = kRcLongW | (cnt << 8); pc.cum = cum; pc.row_off = (int)R.rowmap.size(); pc.ent_off = (int)R.lptr.size() - 1;
+                cum += cnt * rc_cost_of(kRcLongW);
                 for (int k = 0; k < cnt; ++k) {
                     const RcRowIn &rw = rows[i0 + k];
                     R.rowmap.push_back(rw.code);
@@ -94,6 +98,7 @@ static void rc_append(HRc &R, std::vector<RcRowIn> rows, int nlevels, Entries en
             i0 = i1;
         }
         R.levp.push_back((int)R.pieces.size());
+        R.levb.push_back(cum);
         R.nlev++;
     }
 }
@@ -114,6 +119,7 @@ static HRc build_rc(const HCsr &A, int maxw)
 
 static bool rc_fits(const HRc &R)
 {
+    for (auto &pc : R.pieces) if ((pc.wn >> 8) >= (1 << 22)) return false;
     return R.nlev <= kRcMaxLev && R.pieces.size() < 32000 && R.col.size() < (size_t)INT32_MAX && R.lcol.size() < (size_t)INT32_MAX &&
            R.rowmap.size() < (size_t)INT32_MAX;
 }
@@ -124,6 +130,7 @@ static cudaError_t upload_rc(DevArena &ar, const HRc &h, DevRc &d)
     memset(&d, 0, sizeof d);
     d.nlev = h.nlev; d.npieces = (int)h.pieces.size(); d.nfwd_lev = h.nfwd_lev;
     for (int l = 0; l <= h.nlev && l < kRcMaxLev + 2; ++l) d.levp[l] = (short)h.levp[l];
+    for (int l = 0; l < h.nlev && l < kRcMaxLev + 1; ++l) d.levb[l] = h.levb[l];
     for (int p = 0; p < d.npieces && p < kRcInline; ++p) d.inl[p] = h.pieces[p];
     if ((e = ar.upload(&d.pieces, h.pieces)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.rowmap, h.rowmap)) != cudaSuccess) return e;

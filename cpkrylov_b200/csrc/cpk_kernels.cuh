@@ -30,9 +30,110 @@ struct PhaseClock {
 // mutable across phases of the persistent kernel -> plain (coherent) loads.
 // Epi is called as epi(row, sum) by the lane that owns the row.
 // ---------------------------------------------------------------------------
+// The same walk over PACKED entries (DevSell::pk: 16-bit column offset from the row + index into
+// the table of distinct values, 4 bytes per entry instead of 12).  The column of an entry needs
+// the row of its lane, i.e. the slice the entry belongs to: a decode cursor runs over the chunk
+// ahead of the accumulating cursor (slice ends and row maps are one slice ahead in registers
+// either way).
+#ifndef CPK_SPMV_UP
+#define CPK_SPMV_UP 8
+#endif
+template <class Team, class Epi>
+__device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, const double *x, Epi &&epi)
+{
+    const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;
+    int sa, sb;
+    {
+        const int *split = A.wsplit[Team::kKind];
+        if (split != nullptr && A.nws[Team::kKind] == nwarps) {
+            sa = __ldg(&split[gwarp]); sb = __ldg(&split[gwarp + 1]);
+        } else {
+            sa = (int)((long long)A.nslices * gwarp / nwarps);
+            sb = (int)((long long)A.nslices * (gwarp + 1) / nwarps);
+        }
+    }
+    if (sa < sb) {
+        int s = sa;
+        int k = __ldg(&A.sptr[sa]);
+        const int kb = __ldg(&A.sptr[sb]);
+        int send = __ldg(&A.sptr[s + 1]);
+        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+        int row = __ldg(&A.rowmap[s * 32 + lane]);
+        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+        double acc = 0.0;
+        constexpr int U = CPK_SPMV_UP;
+        unsigned ee[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int kk = k + 32 * u + lane;
+            ee[u] = (kk < kb) ? __ldg(&A.pk[kk]) : 0u;
+        }
+        while (k < kb) {
+            unsigned en[U];
+            double xv[U], vv[U];
+            const int k2 = k + 32 * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = k2 + 32 * u + lane;
+                en[u] = (kk < kb) ? __ldg(&A.pk[kk]) : 0u;
+            }
+            // decode: row of every entry of the chunk (a chunk seldom crosses more than one slice end)
+            {
+                int sd = s, sendd = send, send2d = send2, rowd = row, row2d = row2;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k0 = k + 32 * u;              // warp-uniform
+                    if (k0 < kb) {
+                        while (k0 >= sendd) {
+                            ++sd; sendd = send2d; rowd = row2d;
+                            send2d = (sd + 2 <= sb) ? __ldg(&A.sptr[sd + 2]) : kb;
+                            row2d = (sd + 1 < sb) ? __ldg(&A.rowmap[(sd + 1) * 32 + lane]) : -1;
+                        }
+                        const int col = max(rowd, 0) + (int)(short)(ee[u] & 0xffffu);
+                        xv[u] = x[col];
+                        vv[u] = __ldg(&A.dict[ee[u] >> 16]);
+                    } else { xv[u] = 0.0; vv[u] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k0 = k + 32 * u;
+                if (k0 < kb) {
+                    while (k0 >= send) {                    // slice s is complete (possibly empty ones follow)
+                        if (row >= 0) epi(row, acc);
+                        acc = 0.0; ++s;
+                        send = send2; row = row2;
+                        send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
+                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+                    }
+                    acc += vv[u] * xv[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) ee[u] = en[u];
+            k = k2;
+        }
+        while (s < sb) {
+            if (row >= 0) epi(row, acc);
+            acc = 0.0; ++s;
+            row = row2;
+            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+        }
+    }
+    for (int r = gwarp; r < A.nlong; r += nwarps) {
+        const int beg = __ldg(&A.lptr[r]), end = __ldg(&A.lptr[r + 1]);
+        double acc = 0.0;
+        for (int kk = beg + lane; kk < end; kk += 32) acc += __ldg(&A.lval[kk]) * x[__ldg(&A.lcol[kk])];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == 0) epi(__ldg(&A.lrow[r]), acc);
+    }
+}
+
 template <class Team, class Epi>
 __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
+    if (A.pk != nullptr) { spmv_sell_packed(T, A, x, epi); return; }
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
     // range are one contiguous span, walked in chunks of U entries per lane with

@@ -58,7 +58,6 @@ __device__ __forceinline__ int vec_mode(const VecIn &v) { return (v.add ? 1 : 0)
 
 // ---------------------------------------------------------------------------
 // The pass.  `Op` supplies
-//     kB0..kB3                                   rows per batch for widths 0..3 (x 32 lanes)
 //     struct Pre, struct Raw                     row inputs / one gathered operand, as loaded
 //     Pre    pre(int pos, int code)              loads only (code >= 0)
 //     Raw    gather(int colcode)                 loads only
@@ -84,176 +83,159 @@ struct RcPtr {                      // the streamed arrays, in registers
     __device__ __forceinline__ explicit RcPtr(const DevRc &R) : rowmap(R.rowmap), col(R.col), val(R.val) {}
 };
 
+// the streamed data of one batch of B groups of width W, in registers
+template <int W, int B>
+struct RcStream {
+    int code[B], cc[B][W > 0 ? W : 1];
+    double vv[B][W > 0 ? W : 1];
+    __device__ __forceinline__ void load(const RcPtr A, int row_off, int ent_off, int stride, int ng, int batch, int lane) {
+        const int ga = batch * B;
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            const bool on = ga + q < ng;                    // warp-uniform; a surplus slot re-reads the batch's first group
+            const int g = on ? ga + q : ga;
+            code[q] = ldg_stream(&A.rowmap[row_off + g * 32 + lane]);
+            if (!on) code[q] = -1;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                cc[q][j] = ldg_stream(&A.col[ent_off + j * stride + g * 32 + lane]);
+                vv[q][j] = ldg_stream(&A.val[ent_off + j * stride + g * 32 + lane]);
+            }
+        }
+    }
+};
+
+// batches [a, b) of a piece of width W, B groups of 32 rows each.  The streamed loads of batch
+// j+1 are issued before the row inputs and gathers of batch j are consumed (software pipeline
+// in registers): one exposed round trip per batch instead of two.
 template <int W, int B, class Op>
-__device__ __forceinline__ void rc_run_fixed(const RcPtr A, const RcPiece pc, int ga, int gb, int lane, Op &op)
+__device__ __forceinline__ void rc_run_fixed(const RcPtr A, const RcPiece pc, int a, int b, int lane, Op &op)
 {
     constexpr int WW = W > 0 ? W : 1;
-    const int stride = pc.ngroups * 32;
-    int code[B], cc[B][WW];
-    double vv[B][WW];
-    // ---- round trip 1: the streamed data of the whole batch ---------------------------------
+    const int ng = pc.wn >> 8, stride = ng * 32;
+    RcStream<W, B> cur;
+    cur.load(A, pc.row_off, pc.ent_off, stride, ng, a, lane);
+    for (int j = a; j < b; ++j) {
+        RcStream<W, B> nxt;
+        if (j + 1 < b) nxt.load(A, pc.row_off, pc.ent_off, stride, ng, j + 1, lane);
+        else nxt = cur;
+        // ---- row inputs and gathers of the whole batch, loads only -------------------------
+        typename Op::Pre P[B];
+        typename Op::Raw G[B][WW];
 #pragma unroll
-    for (int q = 0; q < B; ++q) {
-        const bool on = ga + q < gb;                        // warp-uniform
-        const int pos = pc.row_off + (on ? ga + q : ga) * 32 + lane;
-        code[q] = ldg_stream(&A.rowmap[pos]);
-        if (!on) code[q] = -1;
+        for (int q = 0; q < B; ++q) {
+            const int g = j * B + q < ng ? j * B + q : j * B;
+            P[q] = op.pre(pc.row_off + g * 32 + lane, cur.code[q] < 0 ? 0 : cur.code[q]);      // dead lanes read row 0 (never finished)
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            const int e = pc.ent_off + j * stride + (on ? ga + q : ga) * 32 + lane;
-            cc[q][j] = ldg_stream(&A.col[e]); vv[q][j] = ldg_stream(&A.val[e]);
+            for (int w = 0; w < W; ++w) G[q][w] = op.gather(cur.cc[q][w]);     // padding lanes hold column 0: a valid address
         }
-    }
-    // ---- round trip 2: row inputs and gathers of the whole batch, loads only ---------------
-    typename Op::Pre P[B];
-    typename Op::Raw G[B][WW];
+        // ---- arithmetic and stores -------------------------------------------------------------
 #pragma unroll
-    for (int q = 0; q < B; ++q) {
-        const int cd = code[q] < 0 ? 0 : code[q];           // dead lanes read row 0 (never finished)
-        P[q] = op.pre(pc.row_off + (ga + q < gb ? ga + q : ga) * 32 + lane, cd);
+        for (int q = 0; q < B; ++q) {
+            double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < W; ++j) G[q][j] = op.gather(cc[q][j]);         // padding lanes hold column 0: a valid address
-    }
-    // ---- arithmetic and stores ---------------------------------------------------------------
-#pragma unroll
-    for (int q = 0; q < B; ++q) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) s += vv[q][j] * op.value(cc[q][j], G[q][j]);
-        if (code[q] >= 0) op.fin(pc.row_off + (ga + q) * 32 + lane, code[q], P[q], s);
+            for (int w = 0; w < W; ++w) s += cur.vv[q][w] * op.value(cur.cc[q][w], G[q][w]);
+            if (cur.code[q] >= 0) op.fin(pc.row_off + (j * B + q) * 32 + lane, cur.code[q], P[q], s);
+        }
+        cur = nxt;
     }
 }
 
-// any width: entries in chunks of CH per lane; the columns of the next chunk are requested as
-// soon as the gathers of the current one are issued (1 + ceil(W / CH) round trips per group)
-#ifndef CPK_RC_CH
-#define CPK_RC_CH 4
-#endif
+// any width: groups [a, b), entries in chunks of CH per lane; the columns of the next chunk are
+// requested as soon as the gathers of the current one are issued
 template <class Op>
-__device__ __forceinline__ void rc_run_wide(const RcPtr A, const RcPiece pc, int g, int lane, Op &op)
+__device__ __forceinline__ void rc_run_wide(const RcPtr A, const RcPiece pc, int a, int b, int lane, Op &op)
 {
     constexpr int CH = CPK_RC_CH;
-    const int W = pc.width, stride = pc.ngroups * 32;
-    const int pos = pc.row_off + g * 32 + lane;
-    const int e0 = pc.ent_off + g * 32 + lane;
-    const int code = ldg_stream(&A.rowmap[pos]);
-    int c[CH]; double v[CH];
-#pragma unroll
-    for (int u = 0; u < CH; ++u) {
-        const int j = u < W ? u : 0;                        // W >= 1 here
-        c[u] = ldg_stream(&A.col[e0 + j * stride]); v[u] = ldg_stream(&A.val[e0 + j * stride]);
-    }
-    const typename Op::Pre P = op.pre(pos, code < 0 ? 0 : code);
-    double s = 0.0;
-    for (int j0 = 0; j0 < W; j0 += CH) {
-        typename Op::Raw G[CH];
-        int cn[CH]; double vn[CH];
-#pragma unroll
-        for (int u = 0; u < CH; ++u) G[u] = op.gather(c[u]);
+    const int W = pc.wn & 255, stride = (pc.wn >> 8) * 32;
+    for (int g = a; g < b; ++g) {
+        const int pos = pc.row_off + g * 32 + lane;
+        const int e0 = pc.ent_off + g * 32 + lane;
+        const int code = ldg_stream(&A.rowmap[pos]);
+        int c[CH]; double v[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
-            const int j = j0 + CH + u < W ? j0 + CH + u : 0;
-            cn[u] = ldg_stream(&A.col[e0 + j * stride]); vn[u] = ldg_stream(&A.val[e0 + j * stride]);
+            const int j = u < W ? u : 0;                    // W >= 4 here
+            c[u] = ldg_stream(&A.col[e0 + j * stride]); v[u] = ldg_stream(&A.val[e0 + j * stride]);
+        }
+        const typename Op::Pre P = op.pre(pos, code < 0 ? 0 : code);
+        double s = 0.0;
+        for (int j0 = 0; j0 < W; j0 += CH) {
+            typename Op::Raw G[CH];
+            int cn[CH]; double vn[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) G[u] = op.gather(c[u]);
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int j = j0 + CH + u < W ? j0 + CH + u : 0;
+                cn[u] = ldg_stream(&A.col[e0 + j * stride]); vn[u] = ldg_stream(&A.val[e0 + j * stride]);
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) if (j0 + u < W) s += v[u] * op.value(c[u], G[u]);
+#pragma unroll
+            for (int u = 0; u < CH; ++u) { c[u] = cn[u]; v[u] = vn[u]; }
+        }
+        if (code >= 0) op.fin(pos, code, P, s);
+    }
+}
+
+// long rows [a, b): one warp per row, lane-strided partial sums + butterfly
+template <class Op>
+__device__ __forceinline__ void rc_run_long(const DevRc &R, const RcPiece pc, int a, int b, int lane, Op &op)
+{
+    for (int r = a; r < b; ++r) {
+        const int pos = pc.row_off + r;
+        const int code = __ldg(&R.rowmap[pos]);             // warp-uniform, >= 0
+        const int beg = __ldg(&R.lptr[pc.ent_off + r]), end = __ldg(&R.lptr[pc.ent_off + r + 1]);
+        const typename Op::Pre P = op.pre(pos, code);
+        double s = 0.0;
+        for (int k = beg + lane; k < end; k += 64) {
+            const bool two = k + 32 < end;
+            const int c0 = __ldg(&R.lcol[k]); const double v0 = __ldg(&R.lval[k]);
+            const int c1 = __ldg(&R.lcol[two ? k + 32 : k]); const double v1 = __ldg(&R.lval[two ? k + 32 : k]);
+            const typename Op::Raw g0 = op.gather(c0), g1 = op.gather(c1);
+            s += v0 * op.value(c0, g0);
+            if (two) s += v1 * op.value(c1, g1);
         }
 #pragma unroll
-        for (int u = 0; u < CH; ++u) if (j0 + u < W) s += v[u] * op.value(c[u], G[u]);
-#pragma unroll
-        for (int u = 0; u < CH; ++u) { c[u] = cn[u]; v[u] = vn[u]; }
-    }
-    if (code >= 0) op.fin(pos, code, P, s);
-}
-
-// long rows: one warp per row, lane-strided partial sums + butterfly
-template <class Op>
-__device__ __forceinline__ void rc_run_long(const DevRc &R, const RcPiece pc, int r, int lane, Op &op)
-{
-    const int pos = pc.row_off + r;
-    const int code = __ldg(&R.rowmap[pos]);                 // warp-uniform, >= 0
-    const int beg = __ldg(&R.lptr[pc.ent_off + r]), end = __ldg(&R.lptr[pc.ent_off + r + 1]);
-    const typename Op::Pre P = op.pre(pos, code);
-    double s = 0.0;
-    for (int k = beg + lane; k < end; k += 64) {
-        const bool two = k + 32 < end;
-        const int c0 = __ldg(&R.lcol[k]); const double v0 = __ldg(&R.lval[k]);
-        const int c1 = __ldg(&R.lcol[two ? k + 32 : k]); const double v1 = __ldg(&R.lval[two ? k + 32 : k]);
-        const typename Op::Raw g0 = op.gather(c0), g1 = op.gather(c1);
-        s += v0 * op.value(c0, g0);
-        if (two) s += v1 * op.value(c1, g1);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (lane == 0) op.fin(pos, code, P, s);
-}
-
-template <int b0, int b1, int b2, int b3> struct RcBatch { static constexpr int kB0 = b0, kB1 = b1, kB2 = b2, kB3 = b3; };
-#define CPK_RC_DIGITS(v) (v) / 1000 % 10, (v) / 100 % 10, (v) / 10 % 10, (v) % 10
-
-template <class Op>
-__device__ __forceinline__ int rc_batch(int width)
-{
-    return width == 0 ? Op::kB0 : width == 1 ? Op::kB1 : width == 2 ? Op::kB2 : width == 3 ? Op::kB3 : 1;
-}
-// asks the streamed lines (row codes, columns, values) of groups [ga, gb) of a piece into L2
-__device__ __forceinline__ void rc_prefetch(const RcPtr A, const RcPiece pc, int ga, int gb, int lane)
-{
-    if (pc.width < 0) return;
-    const int nB = gb - ga, W = pc.width, stride = pc.ngroups * 32;
-    const int L = nB * (1 + 3 * W);
-    for (int t = lane; t < L; t += 32) {
-        const int q = t % nB, r = t / nB;
-        const char *ptr;
-        if (r == 0) ptr = reinterpret_cast<const char *>(&A.rowmap[pc.row_off + (ga + q) * 32]);
-        else if (r <= W) ptr = reinterpret_cast<const char *>(&A.col[pc.ent_off + (r - 1) * stride + (ga + q) * 32]);
-        else { const int r3 = r - 1 - W; ptr = reinterpret_cast<const char *>(&A.val[pc.ent_off + (r3 >> 1) * stride + (ga + q) * 32]) + (r3 & 1) * 128; }
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) op.fin(pos, code, P, s);
     }
 }
 
-// One level.  The batches (a few consecutive groups of one piece) of all pieces of the level
-// form one sequence and are dealt round robin: warp w takes the batches b = w (mod nwarps), so
-// that every warp walks the same number of batches (+-1) -- round trips, not bytes, are what
-// must be equal.
+// One level.  The batches of all its pieces form one sequence, each weighted by its cost in round
+// trips (prefix sums in the piece table); warp w takes the batches that start inside the cost range
+// [T*w/nwarps, T*(w+1)/nwarps): equal numbers of round trips -- not bytes -- for every warp, and
+// consecutive batches of one piece, so that rc_run_fixed can pipeline them.
 template <class Op>
 __device__ __forceinline__ void rc_level(const DevRc &R, int lev, int gwarp, int nwarps, int lane, Op &op)
 {
     const RcPtr A(R);
-    const int p0 = R.levp[lev], p1 = R.levp[lev + 1];
-#ifdef CPK_RC_PREFETCH
-    {
-        // every streamed line this warp will read in the level is asked into L2 first, so that only
-        // the first round trip of the level ends in HBM
-        int b0 = 0;
-        for (int p = p0; p < p1; ++p) {
-            const RcPiece pc = R.piece(p);
-            const int B = rc_batch<Op>(pc.width);
-            const int nb = (pc.ngroups + B - 1) / B;
-            int j = (gwarp - b0) % nwarps;
-            if (j < 0) j += nwarps;
-            for (; j < nb; j += nwarps) rc_prefetch(A, pc, j * B, min(j * B + B, pc.ngroups), lane);
-            b0 = (b0 + nb) % nwarps;
-        }
-    }
-#endif
-    int b0 = 0;                             // first batch of the piece in the level's sequence (mod nwarps)
-    for (int p = p0; p < p1; ++p) {
+    const unsigned T = (unsigned)R.levb[lev];
+    // floor(T * w / nwarps) without 64-bit division (remainder * w < 2^26)
+    const unsigned q = T / (unsigned)nwarps, rem = T % (unsigned)nwarps;
+    const int lo = (int)(q * (unsigned)gwarp + rem * (unsigned)gwarp / (unsigned)nwarps);
+    const int hi = (int)(q * (unsigned)(gwarp + 1) + rem * (unsigned)(gwarp + 1) / (unsigned)nwarps);
+    if (lo >= hi) return;
+    const int p1 = R.levp[lev + 1];
+    for (int p = R.levp[lev]; p < p1; ++p) {
         const RcPiece pc = R.piece(p);
-        const int B = rc_batch<Op>(pc.width);
-        const int nb = (pc.ngroups + B - 1) / B;
-        int j = (gwarp - b0) % nwarps;
-        if (j < 0) j += nwarps;
-        for (; j < nb; j += nwarps) {
-            const int ga = j * B, gb = min(ga + B, pc.ngroups);
-            switch (pc.width) {
-                case 0: rc_run_fixed<0, Op::kB0>(A, pc, ga, gb, lane, op); break;
-                case 1: rc_run_fixed<1, Op::kB1>(A, pc, ga, gb, lane, op); break;
-                case 2: rc_run_fixed<2, Op::kB2>(A, pc, ga, gb, lane, op); break;
-                case 3: rc_run_fixed<3, Op::kB3>(A, pc, ga, gb, lane, op); break;
-                default:
-                    if (pc.width < 0) rc_run_long(R, pc, j, lane, op);
-                    else rc_run_wide(A, pc, j, lane, op);
-            }
+        if (pc.cum >= hi) break;
+        const int width = pc.wn & 255, ng = pc.wn >> 8;
+        const int B = rc_batch_of(width), c = rc_cost_of(width);
+        const int nb = (ng + B - 1) >> (B >> 1);            // B = 1, 2, 4
+        // batch j of the piece starts at cost cum + j*c: the warp takes those that start in [lo, hi)
+        const int a = lo > pc.cum ? (lo - pc.cum + c - 1) / c : 0;
+        const int b = min((hi - pc.cum + c - 1) / c, nb);
+        if (a >= b) continue;
+        switch (width) {
+            case 0: rc_run_fixed<0, rc_batch_of(0)>(A, pc, a, b, lane, op); break;
+            case 1: rc_run_fixed<1, rc_batch_of(1)>(A, pc, a, b, lane, op); break;
+            case 2: rc_run_fixed<2, rc_batch_of(2)>(A, pc, a, b, lane, op); break;
+            case 3: rc_run_fixed<3, rc_batch_of(3)>(A, pc, a, b, lane, op); break;
+            case kRcLongW: rc_run_long(R, pc, a, b, lane, op); break;
+            default: rc_run_wide(A, pc, a, b, lane, op);
         }
-        b0 = (b0 + nb) % nwarps;
     }
 }
 
@@ -266,33 +248,26 @@ __device__ __forceinline__ void rc_level(const DevRc &R, int lev, int gwarp, int
 //                                      forward work) -> out
 // Arithmetic as in the item walks (opLDL2.m:86, right to left).
 // ---------------------------------------------------------------------------
-#ifndef CPK_RC_SWEEP_B            // four digits: rows per batch of the sweep passes for widths 0, 1, 2, 3
-#define CPK_RC_SWEEP_B 4221
-#endif
-#ifndef CPK_RC_RESID_B            // same for the residual pass
-#define CPK_RC_RESID_B 2221
-#endif
-
 template <bool FWD, bool ACC, int MODE>
-struct SweepOp : RcBatch<CPK_RC_DIGITS(CPK_RC_SWEEP_B)> {
+struct SweepOp {
     VecEval<MODE> in;
     const double *dpos;             // D per position
-    double *wv, *yv, *out;
+    double *wy, *out;               // [w (N) | y (N)], both halves indexed by the user index
+    int N;
     struct Raw { VecRaw<MODE> r; };
     struct Pre { VecRaw<MODE> b; double dd, o; };
     __device__ __forceinline__ Raw gather(int c) const {
-        const int src = c >> RC_IDX_BITS, i = c & RC_IDX_MASK;
-        const bool isin = src == RC_SRC_IN;
+        const bool isin = (c >> RC_IDX_BITS) != 0;
+        const int i = c & RC_IDX_MASK;
         Raw g;
-        const double *p = src == RC_SRC_Y ? yv : (src == RC_SRC_W ? wv : in.z);
+        const double *p = isin ? in.z : wy;
         g.r.z = p[i];
         if constexpr ((MODE & 1) != 0) g.r.a = isin ? in.add[i] : 0.0;
         if constexpr ((MODE & 2) != 0) g.r.s = isin ? in.sub[i] : 0.0;
         return g;
     }
     __device__ __forceinline__ double value(int c, const Raw &g) const {
-        const int src = c >> RC_IDX_BITS, i = c & RC_IDX_MASK;
-        return src == RC_SRC_IN ? in.value(i, g.r) : g.r.z;
+        return (c >> RC_IDX_BITS) != 0 ? in.value(c & RC_IDX_MASK, g.r) : g.r.z;
     }
     __device__ __forceinline__ Pre pre(int pos, int code) const {
         const int i = code & RC_IDX_MASK, fl = code >> RC_IDX_BITS;
@@ -300,7 +275,7 @@ struct SweepOp : RcBatch<CPK_RC_DIGITS(CPK_RC_SWEEP_B)> {
         if (FWD) P.b = in.issue(i);
         else {
             const bool direct = (fl & RC_F_WDIRECT) != 0;
-            const double *p = direct ? in.z : wv;
+            const double *p = direct ? in.z : wy;
             P.b.z = p[i];
             if constexpr ((MODE & 1) != 0) P.b.a = direct ? in.add[i] : 0.0;
             if constexpr ((MODE & 2) != 0) P.b.s = direct ? in.sub[i] : 0.0;
@@ -315,14 +290,14 @@ struct SweepOp : RcBatch<CPK_RC_DIGITS(CPK_RC_SWEEP_B)> {
             double acc = in.value(i, P.b) - s;
             if (fl & RC_F_FUSED) {
                 acc = acc / P.dd;                       // column of L is empty: y_i = w_i / d_i
-                if (fl & RC_F_STOREY) yv[i] = acc;
+                if (fl & RC_F_STOREY) wy[N + i] = acc;
                 out[i] = ACC ? P.o + acc : acc;
-            } else wv[i] = acc;
+            } else wy[i] = acc;
         } else {
             const double w = (fl & RC_F_WDIRECT) ? in.value(i, P.b) : P.b.z;
             double acc = w / P.dd;                      // opLDL2.m:86, inv(op.D)
             acc = acc - s;
-            if (fl & RC_F_STOREY) yv[i] = acc;
+            if (fl & RC_F_STOREY) wy[N + i] = acc;
             out[i] = ACC ? P.o + acc : acc;
         }
     }
@@ -336,10 +311,10 @@ __device__ __forceinline__ void ldl_solve_rc_mode(Team &T, const DevLdl &M, cons
     const int nlev = R.nlev, nfwd = R.nfwd_lev;
     for (int lev = 0; lev < nlev; ++lev) {
         if (lev < nfwd) {
-            SweepOp<true, ACC, MODE> op{{}, VecEval<MODE>(in), R.d, M.wv, M.yv, out};
+            SweepOp<true, ACC, MODE> op{VecEval<MODE>(in), R.d, M.wv, out, M.N};
             rc_level(R, lev, gwarp, nwarps, lane, op);
         } else {
-            SweepOp<false, ACC, MODE> op{{}, VecEval<MODE>(in), R.d, M.wv, M.yv, out};
+            SweepOp<false, ACC, MODE> op{VecEval<MODE>(in), R.d, M.wv, out, M.N};
             rc_level(R, lev, gwarp, nwarps, lane, op);
         }
         if (lev + 1 < nlev) T.sync();           // the caller syncs after the last level
@@ -376,7 +351,7 @@ struct NoRider {
 };
 
 template <class Rider, int MODE>
-struct ResidOp : RcBatch<CPK_RC_DIGITS(CPK_RC_RESID_B)> {
+struct ResidOp {
     VecEval<MODE> xin;
     const double *y;
     double *r, *wb;
@@ -409,7 +384,7 @@ template <int MODE, class Team, class Rider>
 __device__ __forceinline__ void resid_phase_mode(Team &T, const DevLdl &M, const VecIn &xin, const double *y,
                                                  double *r, double &rr, double &xx, bool want_xx, Rider &rider, double &extra)
 {
-    ResidOp<Rider, MODE> op{{}, VecEval<MODE>(xin), y, r, xin.wb, want_xx, rider, 0.0, 0.0, 0.0};
+    ResidOp<Rider, MODE> op{VecEval<MODE>(xin), y, r, xin.wb, want_xx, rider, 0.0, 0.0, 0.0};
     rc_level(M.KP, 0, T.gwarp, T.nwarps, T.lane, op);
     rr = op.rr; xx = op.xx; extra = op.extra;
 }
@@ -417,6 +392,20 @@ template <class Team, class Rider>
 __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecIn xin, const double *y,
                                             double *r, double &rr, double &xx, bool want_xx, Rider &rider, double &extra)
 {
+    if (!M.resid_rc) {
+        // K_P in SELL form: the streaming loop of the sparse mat-vec, row work in its epilogue
+        rr = 0.0; xx = 0.0; extra = 0.0;
+        spmv_sell(T, M.KPs, y, [&](int row, double s) {
+            const double xi = xin(row);
+            if (xin.wb) xin.wb[row] = xi;       // pending axpy of the caller lands in memory here
+            const double ri = xi - s;
+            r[row] = ri;
+            rr += ri * ri;
+            if (want_xx) xx += xi * xi;
+            if (Rider::kActive) extra += rider.fin(row, xi, y[row], rider.pre(row));
+        });
+        return;
+    }
     const int mode = vec_mode(xin);
     if (mode == 0) resid_phase_mode<0>(T, M, xin, y, r, rr, xx, want_xx, rider, extra);
     else if (mode == 1) resid_phase_mode<1>(T, M, xin, y, r, rr, xx, want_xx, rider, extra);
@@ -424,7 +413,7 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
 }
 
 // y = K*x for a matrix in row-class form (the `divide` path of opLDL2, opLDL2.m:193-195)
-struct MatvecOp : RcBatch<4, 4, 2, 2> {
+struct MatvecOp {
     const double *x;
     double *y;
     struct Raw { double v; };

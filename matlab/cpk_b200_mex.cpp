@@ -1,8 +1,10 @@
 // cpk_b200_mex.cpp -- thin MEX gateway from MATLAB to libcpk_b200.so.
 //
-// NOT compiled in this repository's CI (no MATLAB / mex.h in the build image); it
-// is the reference-side binding a maintainer builds with
+// The reference-side binding a maintainer builds with
 //     mex -R2018a -I../include cpk_b200_mex.cpp -L../cpkrylov_b200 -lcpk_b200
+// No MATLAB exists in this repository's build image: tests/test_mex_gateway.py compiles this file
+// against the prototype header matlab/stub/mex.h, links it with a toy MEX runtime
+// (matlab/stub/mex_stub.cpp) and drives mexFunction from there.
 // Every branch is a mechanical translation mxArray <-> the plain-pointer C ABI of
 // include/cpk_b200.h; no arithmetic happens here.
 //
@@ -11,7 +13,8 @@
 //   y  = cpk_b200_mex('ldl2_apply', h, z)                     M*z, opLDL2.m:161-188
 //   y  = cpk_b200_mex('ldl2_matvec', h, b)                    M\b, opLDL2.m:193-195
 //   s  = cpk_b200_mex('system_create', A, C, h)               (A, C, M) of method(b1,A,C,M,opts)
-//   [x, niters, solved, status, hist] = cpk_b200_mex('reg_solve', s, solver_id, b, optsvec)
+//   [x, niters, solved, status, hist, t_solve] = cpk_b200_mex('reg_solve', s, solver_id, b, optsvec, [n m])
+//        hist: hist_len x 3 (columns = cg / lq / qr residHistory for cpsymmlq, column 1 otherwise)
 //   h  = cpk_b200_mex('ldl2_create_sqd', G, B, C22, p)        device LDL' with the static permutation p (sequences)
 //        cpk_b200_mex('ldl2_refactor', h, G, B, C22)           next system: new values, same patterns
 //        cpk_b200_mex('system_update', s, A, C)                 ... and its A, C
@@ -139,16 +142,25 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         if (!mxIsNaN(ov[4])) o.restart = (int32_t)ov[4];
         if (!mxIsNaN(ov[5])) o.mem = (int32_t)ov[5];
         const int64_t cap = cpk_hist_capacity(solver, &o);
+        if (nrhs != 6) mexErrMsgIdAndTxt("cpk_b200:arg", "reg_cpkrylov: not enough inputs");       // reg_cpkrylov.m:122-125
         plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
-        mxArray *hist = mxCreateDoubleMatrix((mwSize)cap, 3, mxREAL);     // column-major: 3 rows of the ABI = 3 columns here
+        std::vector<double> hbuf((size_t)3 * (size_t)cap);       // the ABI's 3 rows of `cap` entries
         cpk_stats st;
         const int rc = cpk_reg_solve(s, solver, mxGetDoubles(prhs[3]), &o, mxGetDoubles(plhs[0]), CPK_MEM_HOST,
-                                     &st, mxGetDoubles(hist), cap);
+                                     &st, hbuf.data(), cap);
         fail_if(rc);
         if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)st.niters);
         if (nlhs > 2) plhs[2] = mxCreateLogicalScalar(st.solved != 0);
         if (nlhs > 3) plhs[3] = mxCreateDoubleScalar((double)st.status);
-        if (nlhs > 4) { mxSetM(hist, (mwSize)st.hist_len); plhs[4] = hist; } else mxDestroyArray(hist);
+        if (nlhs > 4) {
+            // hist_len x 3, column-major: column r = row r of the ABI buffer, cut to hist_len entries
+            // (shrinking the first dimension of a cap x 3 array in place would leave columns 2 and 3
+            // at their old offsets)
+            const size_t len = (size_t)(st.hist_len < cap ? st.hist_len : cap);
+            plhs[4] = mxCreateDoubleMatrix((mwSize)len, 3, mxREAL);
+            double *h = mxGetDoubles(plhs[4]);
+            for (size_t r = 0; r < 3; ++r) std::memcpy(h + r * len, hbuf.data() + r * (size_t)cap, sizeof(double) * len);
+        }
         if (nlhs > 5) plhs[5] = mxCreateDoubleScalar(st.t_solve_ms * 1e-3);
     } else if (cmd == "destroy") {
         fail_if(cpk_destroy(as_handle(prhs[1])));

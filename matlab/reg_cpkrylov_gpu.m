@@ -33,8 +33,18 @@ function [x, stats, flag] = reg_cpkrylov_gpu(method, b, A, B, C, G, opts)
     for k = 1:6
         if isfield(opts, f{k}), ov(k) = double(opts.(f{k})); end
     end
-    [x, niters, solved, status, hist] = cpk_b200_mex('reg_solve', hS, ids.(name), b(:), ov, [n m]);
+    [x, niters, solved, status, hist, tdev] = cpk_b200_mex('reg_solve', hS, ids.(name), b(:), ov, [n m]);
     stats.niters = niters;
+    stats.t_device = tdev;                                        % CUDA-event time of the one launch
+    doprint = true;                                               % default of every solver (e.g. cpminres.m:110)
+    if isfield(opts, 'print'), doprint = opts.print; end
+    if doprint
+        % the reference prints one line per iteration from inside the loop (cpminres.m:167-173,
+        % 239-241); the device loop cannot, so the table is printed from the returned history
+        fprintf('\n**** %s on B200 ****\n\n%5s  %9s\n', name, 'iter', '|resid|');
+        for k = 1:size(hist,1), fprintf('%5d  %9.2e\n', k-1, hist(k,1)); end
+        fprintf('\n');
+    end
     if strcmp(name, 'cpsymmlq')                                   % cpsymmlq.m:363-366
         stats.cgresidHistory = hist(:,1); stats.lqresidHistory = hist(:,2); stats.qrresidHistory = hist(:,3);
     else

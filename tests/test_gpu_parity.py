@@ -76,11 +76,11 @@ def test_exprog2_nonsymmetric(cp, meth, extra, kind, team):
 @pytest.mark.parametrize("team", ["cta", "grid"])
 @pytest.mark.parametrize("env", [{"CPK_LDL_SYNCFREE": "1"}, {"CPK_LDL_NO_SHORTCUTS": "1"}, {"CPK_LDL_NO_TAIL": "1"},
                                  {"CPK_LDL_SYNCFREE": "1", "CPK_LDL_NO_TAIL": "1"}, {}, {"CPK_LDL_COMPACT": "1"},
-                                 {"CPK_LDL_RC": "0"}, {"CPK_LDL_RC": "0", "CPK_LDL_NO_TAIL": "1"}])
+                                 {"CPK_LDL_RC": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_TAIL": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_SHORTCUTS": "1"}])
 def test_ldl_walk_variants_agree(cp, env, team):
-    """The LDL' solve has four walks (row-class passes for shallow sweeps with a diagonal D,
-    level-synchronous and sync-free/tagged walks of the item list -- CPK_LDL_RC=0 keeps the
-    row-class form out --, and the shared-memory compact walk of the one-CTA team) and
+    """The LDL' solve has four walks (level-synchronous and sync-free/tagged walks of the item
+    list, row-class passes for shallow sweeps with a diagonal D -- CPK_LDL_RC=1 --, and the
+    shared-memory compact walk of the one-CTA team) and
     setup shortcuts (trivial/fused
     rows, tail inversion); every combination must give the oracle's answer (the
     switches are read when the operator is created).  The global-memory walks of the
@@ -369,3 +369,35 @@ def test_one_operator_many_systems(cp):
     y = Mg @ np.ones(s["N"])                                # M is still the caller's and alive
     assert np.isfinite(y).all()
     Mg.close()
+
+
+@pytest.mark.parametrize("team", ["cta", "grid"])
+@pytest.mark.parametrize("gen", ["kkt_lap3d", "kkt_convdiff"])
+def test_packed_stencil_matvec(cp, gen, team):
+    """H of the synthetic configurations has 2 resp. 7 distinct values and a band below 2^15: its SELL
+    entries are packed to 4 bytes (column offset + value index).  Products and a whole solve must be
+    bit-identical to the unpacked form (CPK_SELL_PACK=0): the packing is lossless."""
+    from cpkrylov_b200 import synth
+    from cpkrylov_b200.ldl import ldl_superlu
+    w = getattr(synth, gen)(g=14)
+    fac = ldl_superlu(synth.kp_matrix(w))
+    x = np.random.default_rng(3).standard_normal(w["n"])
+    out = {}
+    os.environ["CPK_TEAM"] = team
+    try:
+        for pack in ("1", "0"):
+            os.environ["CPK_SELL_PACK"] = pack
+            M = cp.opLDL2(w["G"], w["B"], -w["C"], factors=fac)
+            S = cp.KktSystem(w["H"], w["C"], M)
+            from cpkrylov_b200.solvers import reg_solve_on
+            # kkt_convdiff has a nonsymmetric H: the symmetric solvers rightly stop with the indefinite error
+            meth = "cpminres" if gen == "kkt_lap3d" else "cpdqgmres"
+            xs, st, fl = reg_solve_on(S, meth, w["rhs"], dict(print=False))
+            out[pack] = (S.matvec(0, x), xs, st["niters"])
+            S.close()
+    finally:
+        os.environ.pop("CPK_TEAM", None)
+        os.environ.pop("CPK_SELL_PACK", None)
+    assert relerr(out["1"][0], w["H"] @ x) < 1e-14
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][1], out["0"][1]) and out["1"][2] == out["0"][2]

@@ -19,15 +19,25 @@ from helpers import kp_of, load_factors, load_system, small_kkt
 
 IDX_BITS = 28
 MASK = (1 << IDX_BITS) - 1
-SRC_Y, SRC_W, SRC_IN = 0, 1, 2
+RC_B = (4, 2, 2, 1)                   # CPK_RC_B: groups per batch for the widths 0..3 (wider: 1)
+LONG_W = 255
 
 
 def _rc(A=None, L=None, d=None, perm=None):
+    import os
+    os.environ["CPK_LDL_RC"] = "1"      # the row-class form of the sweeps is opt-in (item list by default)
+    try:
+        return _rc_impl(A, L, d, perm)
+    finally:
+        os.environ.pop("CPK_LDL_RC", None)
+
+
+def _rc_impl(A, L, d, perm):
     lib = _lib.lib()
     fn = lib.cpk_debug_rc
     fn.restype = ct.c_int
     PC = ct.POINTER(_lib.CscStruct)
-    fn.argtypes = [PC, PC, PC, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)] + [ct.c_void_p] * 9
+    fn.argtypes = [PC, PC, PC, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)] + [ct.c_void_p] * 10
     keep = []
     if L is not None:
         N = d.size
@@ -42,53 +52,75 @@ def _rc(A=None, L=None, d=None, perm=None):
         args = [Ac.ref(), None, None, None]
     sizes = np.zeros(8, dtype=np.int64)
     ps = sizes.ctypes.data_as(ct.POINTER(ct.c_int64))
-    _lib.check(fn(*args, ps, *([None] * 9)))
+    _lib.check(fn(*args, ps, *([None] * 10)))
     have, nlev, nfwd, npieces, nrow, ncol, nlptr, nlcol = (int(v) for v in sizes)
     R = dict(have=have, nlev=nlev, nfwd=nfwd,
-             pieces=np.zeros((npieces, 4), dtype=np.int32), levp=np.zeros(nlev + 1, dtype=np.int32),
+             pieces=np.zeros((npieces, 4), dtype=np.int32), levp=np.zeros(nlev + 1, dtype=np.int32), levb=np.zeros(max(nlev, 1), dtype=np.int32),
              rowmap=np.zeros(nrow, dtype=np.int32), d=np.ones(nrow), col=np.zeros(ncol, dtype=np.int32),
              val=np.zeros(ncol), lptr=np.zeros(nlptr, dtype=np.int32), lcol=np.zeros(nlcol, dtype=np.int32),
              lval=np.zeros(nlcol))
     ptr = lambda a: a.ctypes.data if a.size else None
-    _lib.check(fn(*args, ps, ptr(R["pieces"]), ptr(R["levp"]), ptr(R["rowmap"]), ptr(R["d"]), ptr(R["col"]), ptr(R["val"]),
+    _lib.check(fn(*args, ps, ptr(R["pieces"]), ptr(R["levp"]), ptr(R["levb"]), ptr(R["rowmap"]), ptr(R["d"]), ptr(R["col"]), ptr(R["val"]),
                   ptr(R["lptr"]), ptr(R["lcol"]), ptr(R["lval"])))
     return R
 
 
-def _split(R, lev, nwarps, B=(4, 2, 2, 1)):
-    """(piece, ga, gb) per warp, the way rc_level deals the batches of a level round robin"""
+def _batch(w):
+    return RC_B[w] if 0 <= w <= 3 else 1
+
+
+def _cost(w, ch=4):
+    """rc_cost_of: round trips per batch"""
+    return 1 if w <= 3 else (3 if w == LONG_W else 1 + (w + ch - 1) // ch)
+
+
+def _split(R, lev, nwarps):
+    """(piece, group range) per warp, the way rc_level cuts the batch sequence of a level into
+    equal contiguous ranges (integer arithmetic included)"""
     p0, p1 = int(R["levp"][lev]), int(R["levp"][lev + 1])
+    T = int(R["levb"][lev])
     out = []
     for gw in range(nwarps):
-        b0 = 0
+        q, rem = divmod(T, nwarps)
+        lo = q * gw + rem * gw // nwarps
+        hi = q * (gw + 1) + rem * (gw + 1) // nwarps
         for p in range(p0, p1):
-            w, ng = int(R["pieces"][p][0]), int(R["pieces"][p][1])
-            Bp = B[w] if 0 <= w <= 3 else 1
-            nb = (ng + Bp - 1) // Bp
-            j = (gw - b0) % nwarps
-            while j < nb:
-                out.append((p, j * Bp, min(j * Bp + Bp, ng)))
-                j += nwarps
-            b0 = (b0 + nb) % nwarps
+            wn, cum = int(R["pieces"][p][0]), int(R["pieces"][p][1])
+            if cum >= hi:
+                break
+            w, ng = wn & 255, wn >> 8
+            B, c = _batch(w), _cost(w)
+            nb = (ng + B - 1) // B
+            a = (lo - cum + c - 1) // c if lo > cum else 0
+            b = min((hi - cum + c - 1) // c, nb)
+            if a < b:
+                out.append((p, a * B, min(b * B, ng)))
     return out
 
 
 def _groups_once(R, lev, nwarps):
-    """every group of the level is dealt to exactly one warp, and the warps' batch counts
-    differ by at most one"""
+    """every group of the level is dealt to exactly one warp; the prefix sums of the piece table
+    are the batch counts the device computes"""
+    cum = 0
+    for p in range(int(R["levp"][lev]), int(R["levp"][lev + 1])):
+        wn, c = int(R["pieces"][p][0]), int(R["pieces"][p][1])
+        assert c == cum
+        cum += ((wn >> 8) + _batch(wn & 255) - 1) // _batch(wn & 255) * _cost(wn & 255)
+    assert cum == int(R["levb"][lev])
     seen = {}
     for (p, ga, gb) in _split(R, lev, nwarps):
         for g in range(ga, gb):
             assert (p, g) not in seen
             seen[(p, g)] = 1
-    want = sum(int(R["pieces"][p][1]) for p in range(int(R["levp"][lev]), int(R["levp"][lev + 1])))
+    want = sum(int(R["pieces"][p][0]) >> 8 for p in range(int(R["levp"][lev]), int(R["levp"][lev + 1])))
     assert len(seen) == want
 
 
 def _piece_rows(R, p):
     """yields (position, code, cols, vals) for every live row of piece p"""
-    w, ng, row_off, ent_off = (int(v) for v in R["pieces"][p])
-    if w < 0:
+    wn, _, row_off, ent_off = (int(v) for v in R["pieces"][p])
+    w, ng = wn & 255, wn >> 8
+    if w == LONG_W:
         for r in range(ng):
             pos = row_off + r
             b, e = int(R["lptr"][ent_off + r]), int(R["lptr"][ent_off + r + 1])
@@ -106,7 +138,7 @@ def _piece_rows(R, p):
 
 def _walk_sweeps(R, z, N):
     """ldl_solve_rc: wv / yv / out indexed by the user index"""
-    wv = np.full(N, np.nan); yv = np.full(N, np.nan); out = np.full(N, np.nan)
+    wy = np.full(2 * N, np.nan); out = np.full(N, np.nan)       # [w | y], user-indexed halves
     for lev in range(R["nlev"]):
         fwd = lev < R["nfwd"]
         new_w, new_y = {}, {}
@@ -115,8 +147,8 @@ def _walk_sweeps(R, z, N):
                 i, fl = code & MASK, code >> IDX_BITS
                 s = 0.0
                 for c, v in zip(cols.tolist(), vals.tolist()):
-                    src, j = c >> IDX_BITS, c & MASK
-                    x = yv[j] if src == SRC_Y else (wv[j] if src == SRC_W else z[j])
+                    isin, j = c >> IDX_BITS, c & MASK
+                    x = z[j] if isin else wy[j]
                     assert not np.isnan(x), "gather of a value that no earlier level produced"
                     s += v * x
                 if fwd:
@@ -124,22 +156,22 @@ def _walk_sweeps(R, z, N):
                     if fl & 1:
                         acc = acc / R["d"][pos]
                         if fl & 2:
-                            new_y[i] = acc
+                            new_y[N + i] = acc
                         assert np.isnan(out[i]); out[i] = acc
                     else:
                         assert i not in new_w; new_w[i] = acc
                 else:
-                    base = z[i] if (fl & 1) else wv[i]
+                    base = z[i] if (fl & 1) else wy[i]
                     assert not np.isnan(base)
                     acc = base / R["d"][pos] - s
                     if fl & 2:
-                        new_y[i] = acc
+                        new_y[N + i] = acc
                     assert np.isnan(out[i]); out[i] = acc
         # values of a level become visible after its barrier
         for i, v in new_w.items():
-            wv[i] = v
+            wy[i] = v
         for i, v in new_y.items():
-            yv[i] = v
+            wy[i] = v
     return out
 
 
@@ -215,7 +247,7 @@ def test_rc_plain_matrix():
     y = np.full(K.shape[0], np.nan)
     nlong = 0
     for p in range(int(R["levp"][0]), int(R["levp"][1])):
-        nlong += int(R["pieces"][p][0]) < 0
+        nlong += (int(R["pieces"][p][0]) & 255) == LONG_W
         for pos, code, cols, vals in _piece_rows(R, p):
             assert np.isnan(y[code])
             # storage order = CSR order of the row
