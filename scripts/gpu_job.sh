@@ -1,7 +1,6 @@
 set -x
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_table.jsonl
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2_pytest9.log; cat gpurun_out/r2_pytest9.log
-LIBS="b200 up4 up6 r1" timeout 1500 scripts/ab_r2.sh 2>&1 | tee gpurun_out/r2_ab9.log
-CPK_SELL_PACK=0 LIBS="b200" timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/b200-nopack/' | tee -a gpurun_out/r2_ab9.log
-CPK_LDL_RC=1 CPK_RESID_RC=1 LIBS="b200" timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/b200-rc/' | tee -a gpurun_out/r2_ab9.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/r2_pytest10.log; cat gpurun_out/r2_pytest10.log
+timeout 600 python bench.py > gpurun_out/r2_bench10.json 2> gpurun_out/r2_bench10.err; tail -c 3000 gpurun_out/r2_bench10.json; tail -5 gpurun_out/r2_bench10.err
+timeout 600 python scripts/cusparse_compare.py > gpurun_out/r2_cusparse.json 2> gpurun_out/r2_cusparse.err; cat gpurun_out/r2_cusparse.json; tail -3 gpurun_out/r2_cusparse.err
