@@ -62,6 +62,8 @@ _PD = C.POINTER(C.c_double)
 _PCSC = C.POINTER(CscStruct)
 _PSTATS = C.POINTER(StatsStruct)
 _POPTS = C.POINTER(OptsStruct)
+# int (*cpk_matvec_fn)(void *ctx, const double *v, double *u, int64_t n)
+MATVEC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _PD, _PD, C.c_int64)
 API = [
     ("cpk_version", C.c_int, []),
     ("cpk_device_count", C.c_int, []),
@@ -83,6 +85,7 @@ API = [
     ("cpk_ldl2_refactor", C.c_int, [_H, _PCSC, _PCSC, _PCSC]),
     ("cpk_ldl2_get_factor", C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _PD, _PD]),
     ("cpk_system_create", C.c_int, [C.POINTER(_H), _PCSC, _PCSC, _H]),
+    ("cpk_system_create_op", C.c_int, [C.POINTER(_H), C.c_int64, MATVEC_FN, C.c_void_p, _PCSC, _H]),
     ("cpk_system_update", C.c_int, [_H, _PCSC, _PCSC]),
     ("cpk_system_matvec", C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, _PSTATS]),
     ("cpk_opts_default", None, [_POPTS, C.c_int, C.c_int64, C.c_int64]),

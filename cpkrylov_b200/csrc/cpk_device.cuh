@@ -271,12 +271,28 @@ struct DevStatus {
     unsigned long long phase_cycles[8];
 };
 
+// Matrix-free A (reg_cpkrylov.m:40, "A may be a matrix or a linear operator"): the product A*v is
+// computed by a HOST callback while the persistent kernel stays resident.  Mailbox protocol, one
+// request at a time: thread 0 of the team's first CTA publishes the device address of v and a
+// sequence number in mapped host memory; the host copies v out, runs the callback, copies A*v
+// into `u` and then the sequence number into `ack` on ONE copy stream (so `ack` lands after `u`);
+// thread 0 of every CTA polls `ack`.
+struct DevHostOp {
+    int on;                 // 0: A is the explicit matrix in HC / Hn
+    volatile int *req;      // mapped host memory: [0] sequence number of the pending request
+    volatile long long *req_addr;   // mapped host memory: device address of v
+    const int *ack;         // device memory: sequence number of the last answered request
+    const double *u;        // [n] device memory: A*v of that request
+    long long timeout;      // SM cycles a CTA waits for the host before it gives up (CPK_ERR_TIMEOUT)
+};
+
 struct DevSystem {
     int n, m, N;
     DevSell HC;             // blkdiag(H, C), N x N
     DevSell Hn;             // H alone (n x n) and
     DevSell Cm;             // C alone (m x m): stand-alone matvec
     DevLdl  M;
+    DevHostOp hop;
 };
 
 struct SolveArgs {
@@ -338,6 +354,11 @@ __device__ __forceinline__ void st_tagged(Tagged *p, double v, unsigned long lon
     const unsigned long long lo = (unsigned long long)__double_as_longlong(v);
     asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%0, %1};\n\tst.relaxed.gpu.global.b128 [%2], t;\n\t}"
                  :: "l"(lo), "l"(tag), "l"(p) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ int ld_volatile(const int *p) {
     int v;

@@ -9,11 +9,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <chrono>
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -295,7 +297,22 @@ struct System : Object {
     double *d_hist = nullptr; long long hist_cap = 0;
     double *d_gs = nullptr; long long gs_len = 0;
     uint64_t patH = 0, patC = 0;        // pattern hashes of H and C at create time
+    // matrix-free A (cpk_system_create_op): host callback + mailbox (DevHostOp)
+    cpk_matvec_fn aop = nullptr;
+    void *aop_ctx = nullptr;
+    int *h_mail = nullptr;              // mapped pinned: int seq @0, long long address @8, copy sources: int ack @16, int 1 @24
+    double *h_v = nullptr, *h_u = nullptr;      // pinned n-vectors
+    int *d_ack = nullptr;
+    double *d_u = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int hop_failed = 0;                 // the callback returned nonzero during the last solve
     System() { kind = OBJ_SYSTEM; }
+    ~System() override {
+        if (h_mail) cudaFreeHost(h_mail);
+        if (h_v) cudaFreeHost(h_v);
+        if (h_u) cudaFreeHost(h_u);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
 };
 
 // forward decls of kernels
@@ -1457,6 +1474,7 @@ static int cpk_system_update_impl(cpk_handle h, const cpk_csc *A, const cpk_csc 
     CPK_LAUNCH_LOCK();
     System *S = lookup<System>(h, OBJ_SYSTEM);
     if (!S) return fail(CPK_ERR_ARG, "cpk_system_update: not a system handle");
+    if (S->aop) return fail(CPK_ERR_UNSUPPORTED, "cpk_system_update: the system has a matrix-free A (create a new system)");
     if (!csc_ok(A) || !csc_ok(C)) return fail(CPK_ERR_ARG, "cpk_system_update: bad matrix");
     const int n = S->h.n, m = S->h.m;
     if (A->nrows != n || A->ncols != n || C->nrows != m || C->ncols != m) return fail(CPK_ERR_DIM, "Incompatible dimensions.");
@@ -1614,7 +1632,8 @@ static int cw_place(const DeviceCtx *dc, const DevLdl &m, bool grid, size_t dsm,
 }
 
 template <class KG, class KC>
-static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **params, size_t dsm, float *ms)
+static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **params, size_t dsm, float *ms,
+                       const std::function<int()> &service = nullptr)
 {
     CUDA_TRY(cudaMemsetAsync(dc->ctl, 0, sizeof(TeamCtl), dc->stream));
     CUDA_TRY(cudaEventRecord(dc->ev0, dc->stream));
@@ -1624,6 +1643,7 @@ static int launch_team(DeviceCtx *dc, bool grid, KG kgrid, KC kcta, void **param
         CUDA_TRY(cudaLaunchKernel((const void *)kcta, dim3(1), dim3(kBlock), params, dsm, dc->stream));
     ++g_launches;
     CUDA_TRY(cudaEventRecord(dc->ev1, dc->stream));
+    if (service) { const int rc = service(); if (rc) return rc; }      // matrix-free A: answer the kernel's requests until it ends
     CUDA_TRY(cudaStreamSynchronize(dc->stream));
     if (ms) CUDA_TRY(cudaEventElapsedTime(ms, dc->ev0, dc->ev1));
     return CPK_OK;
@@ -1788,6 +1808,12 @@ int cpk_system_matvec(cpk_handle h, int which, const double *x, double *y, cpk_m
 {
     System *S = lookup<System>(h, OBJ_SYSTEM);
     if (!S || !x || !y || which < 0 || which > 1) return fail(CPK_ERR_ARG, "cpk_system_matvec: bad argument");
+    if (which == 0 && S->aop) {
+        if (mem != CPK_MEM_HOST) return fail(CPK_ERR_UNSUPPORTED, "cpk_system_matvec: a matrix-free A is a host callback (host vectors only)");
+        if (stats) memset(stats, 0, sizeof *stats);
+        const int cb = S->aop(S->aop_ctx, x, y, S->h.n);
+        return cb ? fail(CPK_ERR_ARG, "the operator callback for A*v failed (returned %d)", cb) : CPK_OK;
+    }
     return run_matvec(S->device, which == 0 ? S->h.Hn : S->h.Cm, x, y, mem, stats, S->d_b, S->d_x);
 }
 
@@ -1872,6 +1898,106 @@ static int ensure_buffers(System *S, const Plan &p, int64_t hist_cap)
     return CPK_OK;
 }
 
+// Host side of the DevHostOp mailbox: runs on the calling thread between the launch of the
+// persistent kernel and the end of it.  One request = copy v out, callback, copy A*v in, then the
+// sequence number into `ack` on the same copy stream (so the kernel sees `u` complete).
+static int serve_host_op(System *S, DeviceCtx *dc)
+{
+    const int n = S->h.n;
+    volatile int *seq_p = S->h_mail;
+    volatile long long *addr_p = reinterpret_cast<volatile long long *>(reinterpret_cast<char *>(S->h_mail) + 8);
+    int *ack_src = reinterpret_cast<int *>(reinterpret_cast<char *>(S->h_mail) + 16);
+    int *one_src = reinterpret_cast<int *>(reinterpret_cast<char *>(S->h_mail) + 24);
+    *one_src = 1;
+    int served = 0;
+    S->hop_failed = 0;
+    for (;;) {
+        const int seq = *seq_p;
+        if (seq != served) {
+            const long long addr = *addr_p;
+            CUDA_TRY(cudaMemcpyAsync(S->h_v, reinterpret_cast<const void *>(addr), sizeof(double) * n, cudaMemcpyDeviceToHost, S->copy_stream));
+            CUDA_TRY(cudaStreamSynchronize(S->copy_stream));
+            int cb = 1;
+            try { cb = S->aop(S->aop_ctx, S->h_v, S->h_u, n); } catch (...) { cb = 1; }
+            if (cb != 0) {
+                // stop the kernel: its wait loops and barriers poll the abort flag
+                S->hop_failed = cb;
+                CUDA_TRY(cudaMemcpyAsync(&dc->ctl->abort, one_src, sizeof(int), cudaMemcpyHostToDevice, S->copy_stream));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(S->d_u, S->h_u, sizeof(double) * n, cudaMemcpyHostToDevice, S->copy_stream));
+            }
+            *ack_src = seq;
+            CUDA_TRY(cudaMemcpyAsync(S->d_ack, ack_src, sizeof(int), cudaMemcpyHostToDevice, S->copy_stream));
+            CUDA_TRY(cudaStreamSynchronize(S->copy_stream));      // ack_src is reused by the next request
+            served = seq;
+            continue;
+        }
+        const cudaError_t q = cudaEventQuery(dc->ev1);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { cudaGetLastError(); return fail(CPK_ERR_CUDA, "CUDA error while serving a matrix-free A: %s", cudaGetErrorString(q)); }
+        std::this_thread::yield();
+    }
+    return CPK_OK;
+}
+
+static int cpk_system_create_op_impl(cpk_handle *out, int64_t n_in, cpk_matvec_fn Aop, void *ctx, const cpk_csc *C, cpk_handle Mh)
+{
+    if (!out) return fail(CPK_ERR_ARG, "cpk_system_create_op: null output handle");
+    if (!Aop) return fail(CPK_ERR_ARG, "cpk_system_create_op: null operator callback");
+    Ldl2 *M = lookup<Ldl2>(Mh, OBJ_LDL2);
+    if (!M) return fail(CPK_ERR_ARG, "cpk_system_create_op: M is not an opLDL2 handle");
+    if (!csc_ok(C)) return fail(CPK_ERR_ARG, "cpk_system_create_op: bad matrix");
+    if (C->nrows != C->ncols || n_in != M->d.nA || C->nrows != M->d.nC) return fail(CPK_ERR_DIM, "Incompatible dimensions.");
+    if (M->in_system) return fail(CPK_ERR_ARG, "this opLDL2 handle already belongs to a system (its sweep buffers are not shareable)");
+    const int n = M->d.nA, m = M->d.nC;
+    DeviceCtx *dc;
+    int rc = get_device_ctx(M->device, &dc);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(M->device));
+    HCsr Cr = csr_from_csc(*C);
+    HSell sc = build_sell(Cr);
+    auto o = std::make_unique<System>();
+    o->device = M->device; o->ar.device = M->device; o->war.device = M->device;
+    o->M = M; o->M_handle = Mh;
+    DevSystem &d = o->h;
+    d.n = n; d.m = m; d.N = n + m;
+    memset(&d.HC, 0, sizeof d.HC); memset(&d.Hn, 0, sizeof d.Hn);      // no explicit A: the kernels never walk them (hop.on)
+    d.HC.nrows = d.HC.ncols = n + m; d.Hn.nrows = d.Hn.ncols = n;
+    CUDA_TRY(upload_sell(o->ar, sc, d.Cm));
+    d.M = M->d;
+    CUDA_TRY(o->ar.alloc(&o->d_sys, 1));
+    CUDA_TRY(o->ar.alloc(&o->d_args, 1));
+    CUDA_TRY(o->ar.alloc(&o->d_status, 1, true));
+    CUDA_TRY(o->ar.alloc(&o->d_b, d.N));
+    CUDA_TRY(o->ar.alloc(&o->d_x, d.N));
+    CUDA_TRY(o->ar.alloc(&o->d_u, std::max(n, 1)));
+    CUDA_TRY(o->ar.alloc(&o->d_ack, 1, true));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&o->h_mail), 64, cudaHostAllocMapped));
+    memset(o->h_mail, 0, 64);
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&o->h_v), sizeof(double) * std::max(n, 1)));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&o->h_u), sizeof(double) * std::max(n, 1)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
+    o->aop = Aop; o->aop_ctx = ctx;
+    int *mail_dev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&mail_dev), o->h_mail, 0));
+    d.hop.on = 1;
+    d.hop.req = mail_dev;
+    d.hop.req_addr = reinterpret_cast<volatile long long *>(reinterpret_cast<char *>(mail_dev) + 8);
+    d.hop.ack = o->d_ack;
+    d.hop.u = o->d_u;
+    {
+        // how long a CTA waits for one answer (SM cycles ~ 2 GHz): CPK_HOSTOP_TIMEOUT_S seconds, 120 by default
+        const char *e = getenv("CPK_HOSTOP_TIMEOUT_S");
+        const double sec = e ? atof(e) : 120.0;
+        d.hop.timeout = (long long)(std::max(sec, 0.001) * 2.0e9);
+    }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+    o->patC = pattern_hash(C);
+    M->in_system = true;
+    *out = register_obj(std::move(o));
+    return CPK_OK;
+}
+
 static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *opts, double *x_out, double *dy_out,
                     cpk_mem mem, cpk_stats *stats, double *hist, int64_t hist_cap, int reg_mode)
 {
@@ -1924,7 +2050,15 @@ static int do_solve(cpk_handle h, int solver, const double *b, const cpk_opts *o
     int team_ctas = 0;          // the whole grid is one team
     void *params[] = {(void *)&ps, (void *)&pa, (void *)&dc->ctl, (void *)&dc->partials, (void *)&wide, (void *)&wide_cols, (void *)&team_ctas};
     float ms = 0.f;
-    rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, dsm_total, &ms);
+    if (S->aop) {
+        // a launch numbers its requests from 1: clear the mailbox and the acknowledged number
+        memset(S->h_mail, 0, 64);
+        CUDA_TRY(cudaMemsetAsync(S->d_ack, 0, sizeof(int), dc->stream));
+        rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, dsm_total, &ms,
+                         [&] { return serve_host_op(S, dc); });
+        if (!rc && S->hop_failed) return fail(CPK_ERR_ARG, "the operator callback for A*v failed (returned %d)", S->hop_failed);
+    } else
+        rc = launch_team(dc, grid, solver_kernel(solver, true), solver_kernel(solver, false), params, dsm_total, &ms);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(dc->h_status, S->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost));
     const DevStatus &st = dc->h_status[0];
@@ -1978,6 +2112,7 @@ static int cpk_batch_reg_solve_impl(const cpk_handle *handles, int64_t count, in
         sys[i] = lookup<System>(handles[i], OBJ_SYSTEM);
         if (!sys[i]) return fail(CPK_ERR_ARG, "batch entry %lld is not a system handle", (long long)i);
         if (sys[i]->device != sys[0]->device) return fail(CPK_ERR_ARG, "all systems of a batch must live on one device");
+        if (sys[i]->aop) return fail(CPK_ERR_UNSUPPORTED, "batch entry %lld has a matrix-free A: solve it with cpk_reg_solve", (long long)i);
         for (int64_t j = 0; j < i; ++j)
             if (sys[j] == sys[i]) return fail(CPK_ERR_ARG, "system %lld appears twice in the batch", (long long)i);
     }
@@ -2149,6 +2284,11 @@ int cpk_system_update(cpk_handle h, const cpk_csc *A, const cpk_csc *C)
 int cpk_system_create(cpk_handle *out, const cpk_csc *A, const cpk_csc *C, cpk_handle Mh)
 {
     return guarded([&] { return cpk_system_create_impl(out, A, C, Mh); });
+}
+
+int cpk_system_create_op(cpk_handle *out, int64_t n, cpk_matvec_fn Aop, void *ctx, const cpk_csc *C, cpk_handle Mh)
+{
+    return guarded([&] { return cpk_system_create_op_impl(out, n, Aop, ctx, C, Mh); });
 }
 
 int cpk_batch_reg_solve(const cpk_handle *handles, int64_t count, int solver, const double *const *b, const cpk_opts *opts,

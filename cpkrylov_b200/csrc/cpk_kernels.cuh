@@ -216,6 +216,53 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
 }
 
 // ---------------------------------------------------------------------------
+// blkdiag(A, C) * V for the solver loops (the sparse mtimes call sites cpcg.m:151-152,
+// cpminres.m:187-188, ...): epi(row, sum) for every row of [A*v; C*q].
+// Explicit A: ONE streaming pass over the SELL form of blkdiag(H, C).
+// Matrix-free A (DevHostOp): A*v comes from the host through the mailbox, C*q from the
+// device.  `with_c` = false: only the A rows (rhs shift of reg_cpkrylov.m:157).
+// Entry: V complete and visible to the team (every call site follows a team barrier).
+// `seq` counts the requests of this launch and is carried by every thread.
+// ---------------------------------------------------------------------------
+template <class Team, class Epi>
+__device__ __noinline__ void hostop_mult(Team &T, const DevSystem &S, int &seq, const double *V, bool with_c, Epi &&epi)
+{
+    const DevHostOp &Hh = S.hop;
+    ++seq;
+    if (T.leader()) {
+        __threadfence_system();                 // V (written by other SMs, ordered by the team barrier) before the request
+        *Hh.req_addr = (long long)V;
+        __threadfence_system();
+        *Hh.req = seq;
+    }
+    if (T.cta_leader()) {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_acquire_sys(Hh.ack) != seq) {
+            __nanosleep(500);
+            if ((++spins & 0x3f) == 0) {
+                if (T.aborted()) break;
+                if (clock64() - t0 > Hh.timeout) { T.set_abort(); break; }
+            }
+        }
+    }
+    T.cta_sync();
+    if (T.aborted()) return;
+    TEAM_FOR(T, i, S.n) epi(i, ld_cg(&Hh.u[i]));       // written by the copy engine: never through L1
+    if (with_c) {
+        const int n = S.n;
+        spmv_sell(T, S.Cm, V + n, [&](int row, double s) { epi(n + row, s); });
+    }
+}
+
+template <class Team, class Epi>
+__device__ __forceinline__ void kkt_mult(Team &T, const DevSystem &S, int &seq, const double *V, Epi &&epi)
+{
+    if (S.hop.on) hostop_mult(T, S, seq, V, true, epi);
+    else spmv_sell(T, S.HC, V, epi);
+}
+
+// ---------------------------------------------------------------------------
 // Input of an LDL solve: element i of the vector opLDL2.multiply works on.
 //   value(i) = sgn(i) * z[i] - (sub ? sub[i] : 0)
 // sgn(i) = -1 for i >= nA when neg_tail (the solvers pass [u; -t], e.g.

@@ -22,10 +22,14 @@ struct Ctx {
     DevStatus *st;
     PhaseClock pc;
     int epoch;
+    int hop_seq;            // requests made to a matrix-free A so far (DevHostOp)
     double *dsm;            // dynamic shared memory (doubles)
     int n, m, N;
 
     __device__ double *vec(int i) const { return A.work + (size_t)i * N; }
+    // matrix-free A only: false once the wait for the host's A*v gave up (host error or timeout),
+    // so that the loops end instead of iterating on garbage; explicit matrices never look
+    __device__ bool alive() const { return !S.hop.on || !T.aborted(); }
     __device__ void hist(int row, long long idx, double v) const {
         if (T.leader() && A.hist && idx < A.hist_cap) A.hist[(size_t)row * A.hist_cap + idx] = v;
     }
@@ -36,7 +40,7 @@ struct Ctx {
     __device__ double spmv_dot(const double *V, double *U) {
         pc.mark(CPK_PH_VEC_);
         double part[1] = {0.0};
-        spmv_sell(T, S.HC, V, [&](int row, double s) { U[row] = s; part[0] += s * V[row]; });
+        kkt_mult(T, S, hop_seq, V, [&](int row, double s) { U[row] = s; part[0] += s * V[row]; });
         T.template reduce<1>(part);
         pc.mark(CPK_PH_SPMV_);
         return part[0];
@@ -116,7 +120,7 @@ __device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
     const double stopTol = c.A.atol + c.A.rtol * residNorm;
     c.hist(0, 0, residNorm);
     long long itn = 0;
-    while (residNorm > stopTol && itn < c.A.itmax) {                // :147
+    while (residNorm > stopTol && itn < c.A.itmax && c.alive()) {                // :147
         ++itn;
         const double pAp_qCq = c.spmv_dot(PQ, APCQ);                // :151-152
         const double alpha = rn2 / pAp_qCq;                         // :154
@@ -284,7 +288,7 @@ __device__ void run_cpminres(Ctx<Team> &c, const double *b, double *X)
     double deltabar = 0.0, epsln = 0.0, taubar = beta, cs = -1.0, sn = 0.0;
     const double stopTol = c.A.atol + c.A.rtol * residNorm;
 
-    while (residNorm > stopTol && k < c.A.itmax) {                  // :176
+    while (residNorm > stopTol && k < c.A.itmax && c.alive()) {                  // :176
         ++k;
         { double *t = VKM1; VKM1 = VK; VK = VKP1; VKP1 = t; }       // :181-184
         double alpha, betasq;
@@ -349,7 +353,7 @@ __device__ void run_cpcglanczos(Ctx<Team> &c, const double *b, double *X)
     const double stopTol = c.A.atol + c.A.rtol * residNorm;
     double bstopTol = btol * beta1;
 
-    while (residNorm > stopTol && residNorm > bstopTol && k < c.A.itmax) {      // :221
+    while (residNorm > stopTol && residNorm > bstopTol && k < c.A.itmax && c.alive()) {      // :221
         ++k;
         { double *t = VKM1; VKM1 = VK; VK = VKP1; VKP1 = t; }
         double alpha, betasq;
@@ -440,7 +444,7 @@ __device__ void run_cpsymmlq(Ctx<Team> &c, const double *b, double *X)
         double lqresidNorm, qrresidNorm, den;
         c.hist(0, 0, beta1);                                                    // :331 (prepended)
         long long h = 0;                                                        // entries in lq/qr rows
-        while (cgresidNorm > stopTol && k < c.A.itmax) {                        // :229
+        while (cgresidNorm > stopTol && k < c.A.itmax && c.alive()) {                        // :229
             double matnorm = sqrt(matnorm2);
             double epsmat = matnorm * kEps;
             den = gammabar;
@@ -587,7 +591,7 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
     long long hl = 0;
     int k = 0;
     T.sync();
-    while (!finished && outer < outermax) {                         // :155
+    while (!finished && outer < outermax && c.alive()) {                         // :155
         ++outer;
         double part[1] = {0.0};
         if (outer == 1) {                                           // :160-165
@@ -595,7 +599,7 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
             T.sync();
         } else {                                                    // :166-168
             c.pc.mark(CPK_PH_VEC_);
-            spmv_sell(T, c.S.HC, X, [&](int row, double s) { U[row] = (row < n) ? b[row] - s : s; });
+            kkt_mult(T, c.S, c.hop_seq, X, [&](int row, double s) { U[row] = (row < n) ? b[row] - s : s; });
             T.sync();
             c.pc.mark(CPK_PH_SPMV_);
         }
@@ -616,12 +620,12 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
         k = 0;
         if (T.cta_leader()) g[0] = residNorm;
         T.sync();
-        while (residNorm > stopTol && k < R) {                      // :203
+        while (residNorm > stopTol && k < R && c.alive()) {                      // :203
             ++k;
             const double *Vk = VQ + (size_t)(k - 1) * N;
             double *Vk1 = VQ + (size_t)k * N;
             c.pc.mark(CPK_PH_VEC_);
-            spmv_sell(T, c.S.HC, Vk, [&](int row, double s) { U[row] = s; });   // :209-210
+            kkt_mult(T, c.S, c.hop_seq, Vk, [&](int row, double s) { U[row] = s; });   // :209-210
             T.sync();
             c.pc.mark(CPK_PH_SPMV_);
             c.apply(U, true, W);                                    // :211
@@ -731,7 +735,7 @@ __device__ void run_cpdqgmres(Ctx<Team> &c, const double *b, double *X)
     const double stopTol = c.A.atol + c.A.rtol * residNorm;
     c.hist(0, 0, residNorm);
     T.sync();
-    while (residNorm > stopTol && k < c.A.itmax) {                  // :194
+    while (residNorm > stopTol && k < c.A.itmax && c.alive()) {                  // :194
         ++k;
         const int kpos = (int)((k - 1) % M1);                       // 0-based slots (:199-201)
         const int kp1pos = (int)(k % M1);
@@ -739,7 +743,7 @@ __device__ void run_cpdqgmres(Ctx<Team> &c, const double *b, double *X)
         const double *Vk = VQ + (size_t)kpos * N;
         double *Vk1 = VQ + (size_t)kp1pos * N;
         c.pc.mark(CPK_PH_VEC_);
-        spmv_sell(T, c.S.HC, Vk, [&](int row, double s) { U[row] = s; });       // :205-206
+        kkt_mult(T, c.S, c.hop_seq, Vk, [&](int row, double s) { U[row] = s; });       // :205-206
         T.sync();
         c.pc.mark(CPK_PH_SPMV_);
         c.apply(U, true, W);                                        // :207
@@ -816,7 +820,7 @@ template <int SOLVER, class Team>
 __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, double *dsm)
 {
     SolveArgs A = A0;
-    Ctx<Team> c{T, S, A, A.status, PhaseClock(), 0, dsm, S.n, S.m, S.N};
+    Ctx<Team> c{T, S, A, A.status, PhaseClock(), 0, 0, dsm, S.n, S.m, S.N};
     c.epoch = *S.M.epoch;       // flags of earlier launches carry earlier epochs
     compact_init(T, S.M);
     const int n = S.n, N = S.N;
@@ -837,7 +841,9 @@ __device__ void solve_entry(Team &T, const DevSystem &S, const SolveArgs &A0, do
             VecIn in{B1, nullptr, n, false};
             ldl2_apply(T, S.M, in, XY0, c.epoch, c.st, c.pc);              // :156
             // b1 = b(1:n) - A*xy0(1:n) - B'*xy0(n+1:n+m)                    :157
-            spmv_sell(T, S.Hn, XY0, [&](int row, double s) { B1[row] = A.b[row] - s; });
+            auto shift_epi = [&](int row, double s) { B1[row] = A.b[row] - s; };
+            if (S.hop.on) hostop_mult(T, S, c.hop_seq, XY0, false, shift_epi);
+            else spmv_sell(T, S.Hn, XY0, shift_epi);
             T.sync();
             spmv_sell(T, S.M.K12, XY0 + n, [&](int row, double s) { B1[row] = B1[row] - s; });
             T.sync();

@@ -243,19 +243,52 @@ class KktSystem:
         caller's and outlives the system."""
         if not isinstance(M, opLDL2):
             raise TypeError("M must be a cpkrylov_b200.opLDL2 (GPU operator handle)")
-        if not (sp.issparse(A) or isinstance(A, np.ndarray)):
-            raise TypeError("on the GPU path A must be an explicit matrix "
-                            "(matrix-free A is listed under 'next' in DESIGN.md)")
-        A = sp.csc_matrix(A); Cm = sp.csc_matrix(Cm)
-        self.n, self.m = A.shape[0], Cm.shape[0]
+        Cm = sp.csc_matrix(Cm)
+        self.matrix_free = not (sp.issparse(A) or isinstance(A, np.ndarray))
+        self.n, self.m = int(A.shape[0]), Cm.shape[0]
         self.N = self.n + self.m
         self.M = M
-        a, c = _lib.Csc(A), _lib.Csc(Cm)
+        c = _lib.Csc(Cm)
         h = ct.c_uint64(0)
-        _lib.check(_lib.lib().cpk_system_create(ct.byref(h), a.ref(), c.ref(), M.handle))
+        if self.matrix_free:
+            # reg_cpkrylov.m:40: "A may be a matrix or a linear operator" -- anything with
+            # A @ v (or A.matvec / A * v as a Spot operator has it); the product is a host
+            # callback answered from inside the solve call (cpk_system_create_op)
+            self._Aop = A
+            self._cb_error = None
+            self.n_products = 0
+
+            def _cb(_ctx, v_ptr, u_ptr, n):
+                try:
+                    v = np.ctypeslib.as_array(v_ptr, shape=(n,))
+                    u = np.ctypeslib.as_array(u_ptr, shape=(n,))
+                    if hasattr(A, "matvec"):
+                        r = A.matvec(v)
+                    elif hasattr(A, "__matmul__"):
+                        r = A @ v
+                    else:
+                        r = A * v
+                    u[:] = np.asarray(r, dtype=np.float64).reshape(n)
+                    self.n_products += 1
+                    return 0
+                except BaseException as ex:        # never unwind through the C frames
+                    self._cb_error = ex
+                    return 1
+            self._cb = _lib.MATVEC_FN(_cb)          # keep the thunk alive as long as the system
+            _lib.check(_lib.lib().cpk_system_create_op(ct.byref(h), self.n, self._cb, None, c.ref(), M.handle))
+        else:
+            a = _lib.Csc(sp.csc_matrix(A))
+            _lib.check(_lib.lib().cpk_system_create(ct.byref(h), a.ref(), c.ref(), M.handle))
         self.handle = h
         self.owns_M = bool(owns_M)
         M._owned_by_system = True
+
+    def check_callback(self):
+        """re-raises what the A*v callback raised during the last solve (the C side only sees 'failed')"""
+        ex = getattr(self, "_cb_error", None)
+        if ex is not None:
+            self._cb_error = None
+            raise ex
 
     def update(self, A, Cm):
         """New values of A (= H) and C, same patterns (next system of a sequence)."""

@@ -105,7 +105,9 @@ def _system_of(A, Cm, M):
     pair arrives."""
     if isinstance(A, KktSystem):
         return A
-    key = (_content_key(A), _content_key(Cm))
+    # an operator has no content to hash: it is keyed by identity (the system keeps a reference,
+    # so the id cannot be reused while the cache entry lives)
+    key = (_content_key(A) if (sp.issparse(A) or isinstance(A, np.ndarray)) else ("operator", id(A)), _content_key(Cm))
     sysobj = getattr(M, "_system", None)
     if sysobj is not None and (sysobj.handle is None or sysobj._key != key):
         sysobj.close()                  # frees the device copy of the old (A, C); M stays (it is the caller's)
@@ -129,6 +131,7 @@ def _make_solver(name):
         st = _lib.StatsStruct()
         rc = _lib.lib().cpk_solve(S.handle, sid, b.ctypes.data, ct.byref(o), x.ctypes.data, y.ctypes.data,
                                   _lib.MEM_HOST, ct.byref(st), hist.ctypes.data, cap)
+        S.check_callback()
         stats, flag = _finish(name, st, hist, cap, rc, opts)
         return x, y, stats, flag
     solver.__name__ = name
@@ -188,6 +191,7 @@ def reg_solve_on(S, method, b, opts=None):
     st = _lib.StatsStruct()
     rc = _lib.lib().cpk_reg_solve(S.handle, sid, b.ctypes.data, ct.byref(o), x.ctypes.data, _lib.MEM_HOST,
                                   ct.byref(st), hist.ctypes.data, cap)
+    S.check_callback()
     stats, flag = _finish(name, st, hist, cap, rc, opts)
     stats["stime"] = time.perf_counter() - tstarts
     return x, stats, flag
@@ -224,6 +228,7 @@ def reg_cpkrylov(method, b, A, B, Cm, G, opts=None, factors=None, ldl_method="au
     rc = _lib.lib().cpk_reg_solve(S.handle, sid, b.ctypes.data, ct.byref(o), x.ctypes.data, _lib.MEM_HOST,
                                   ct.byref(st), hist.ctypes.data, cap)
     try:
+        S.check_callback()
         stats, flag = _finish(name, st, hist, cap, rc, opts)
     except Exception:
         S.close()

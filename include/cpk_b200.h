@@ -178,6 +178,20 @@ int  cpk_ldl2_get_factor(cpk_handle M, int64_t *nnz, int64_t *colptr, int64_t *r
  * the same device.  B (m x n) is only used by cpk_reg_solve for the rhs shift
  * B'*y0 (reg_cpkrylov.m:157); it is taken from M. */
 int  cpk_system_create(cpk_handle *S, const cpk_csc *A, const cpk_csc *C, cpk_handle M);
+/* Matrix-free A: reg_cpkrylov.m:40 "the argument A may be a matrix or a linear operator"
+ * (a Spot operator in the reference; the solvers only ever form A*v: cpcg.m:151,
+ * cpcglanczos.m:228, cpminres.m:187, cpsymmlq.m:238, cpgmres.m:209, cpdqgmres.m:205, and the
+ * rhs shift reg_cpkrylov.m:157).  `Aop(ctx, v, u, n)` must write u = A*v for HOST n-vectors and
+ * return 0 (anything else aborts the solve with CPK_ERR_ARG).  The solve stays ONE persistent
+ * kernel with every Krylov vector, the preconditioner apply and the recurrences on the device;
+ * per product only v and A*v cross the bus: the kernel posts a request in mapped host memory,
+ * the calling thread answers it from inside cpk_solve / cpk_reg_solve (the callback runs on
+ * that thread) and the kernel resumes.  The callback must not launch kernels on the handle's
+ * GPU (the resident solver owns every SM) nor call this library.  A CTA waits at most
+ * CPK_HOSTOP_TIMEOUT_S seconds (environment, default 120) for an answer. */
+typedef int (*cpk_matvec_fn)(void *ctx, const double *v, double *u, int64_t n);
+int  cpk_system_create_op(cpk_handle *S, int64_t n, cpk_matvec_fn Aop, void *ctx,
+                          const cpk_csc *C, cpk_handle M);
 /* new values of A (= H) and C with the patterns the system was created with (the other
  * half of a sequence step next to cpk_ldl2_refactor; reg_cpkrylov.m:1 takes A and C anew
  * for every system) */
