@@ -13,6 +13,9 @@
 //   y  = cpk_b200_mex('ldl2_apply', h, z)                     M*z, opLDL2.m:161-188
 //   y  = cpk_b200_mex('ldl2_matvec', h, b)                    M\b, opLDL2.m:193-195
 //   s  = cpk_b200_mex('system_create', A, C, h)               (A, C, M) of method(b1,A,C,M,opts)
+//   s  = cpk_b200_mex('system_create_op', n, Aop, C, h)       A is an operator (Spot object, function handle):
+//                                                             reg_cpkrylov.m:40; A*v is evaluated by mexCallMATLAB
+//                                                             from inside reg_solve while the kernel stays resident
 //   [x, niters, solved, status, hist, t_solve] = cpk_b200_mex('reg_solve', s, solver_id, b, optsvec, [n m])
 //        hist: hist_len x 3 (columns = cg / lq / qr residHistory for cpsymmlq, column 1 otherwise)
 //   h  = cpk_b200_mex('ldl2_create_sqd', G, B, C22, p)        device LDL' with the static permutation p (sequences)
@@ -20,6 +23,7 @@
 //        cpk_b200_mex('system_update', s, A, C)                 ... and its A, C
 //        cpk_b200_mex('destroy', h)
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -53,7 +57,34 @@ static cpk_csc as_csc(const mxArray *a, std::vector<int64_t> &jc, std::vector<in
 
 static cpk_handle as_handle(const mxArray *a) { return (cpk_handle)mxGetScalar(a); }
 
-static void at_exit(void) { cpk_destroy_all(); }
+// Operators of matrix-free systems: persistent copies of the MATLAB objects, by system handle.
+static std::map<cpk_handle, mxArray *> g_ops;
+
+// cpk_matvec_fn: u = A*v through the interpreter.  Runs on the MATLAB thread (the library answers
+// the kernel's requests from inside cpk_reg_solve, i.e. inside this MEX call).
+static int op_matvec(void *ctx, const double *v, double *u, int64_t n)
+{
+    mxArray *op = static_cast<mxArray *>(ctx);
+    mxArray *vin = mxCreateDoubleMatrix((mwSize)n, 1, mxREAL);
+    std::memcpy(mxGetDoubles(vin), v, sizeof(double) * (size_t)n);
+    mxArray *out = nullptr;
+    mxArray *in[2] = {op, vin};
+    // function handle: feval(A, v); anything else (Spot operator, matrix): mtimes(A, v)
+    const int rc = mexCallMATLAB(1, &out, 2, in, mxIsClass(op, "function_handle") ? "feval" : "mtimes");
+    mxDestroyArray(vin);
+    if (rc != 0 || !out) return 1;
+    const bool ok = mxIsDouble(out) && !mxIsSparse(out) && !mxIsComplex(out) && mxGetNumberOfElements(out) == (size_t)n;
+    if (ok) std::memcpy(u, mxGetDoubles(out), sizeof(double) * (size_t)n);
+    mxDestroyArray(out);
+    return ok ? 0 : 2;
+}
+
+static void at_exit(void)
+{
+    cpk_destroy_all();
+    for (auto &kv : g_ops) mxDestroyArray(kv.second);
+    g_ops.clear();
+}
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
@@ -127,6 +158,18 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         cpk_handle s = 0;
         fail_if(cpk_system_create(&s, &a, &c, as_handle(prhs[3])));
         plhs[0] = mxCreateDoubleScalar((double)s);
+    } else if (cmd == "system_create_op") {                       // n, Aop, C, h
+        if (nrhs != 5) mexErrMsgIdAndTxt("cpk_b200:arg", "Invalid number of arguments.");
+        std::vector<int64_t> jc, ir;
+        cpk_csc c = as_csc(prhs[3], jc, ir);
+        mxArray *op = mxDuplicateArray(prhs[2]);
+        mexMakeArrayPersistent(op);
+        cpk_handle s = 0;
+        const int rc = cpk_system_create_op(&s, (int64_t)mxGetScalar(prhs[1]), op_matvec, op, &c, as_handle(prhs[4]));
+        if (rc != CPK_OK) mxDestroyArray(op);
+        fail_if(rc);
+        g_ops[s] = op;
+        plhs[0] = mxCreateDoubleScalar((double)s);
     } else if (cmd == "reg_solve") {                              // s, solver_id, b, [atol rtol btol itmax restart mem] (NaN = absent)
         const cpk_handle s = as_handle(prhs[1]);
         const int solver = (int)mxGetScalar(prhs[2]);
@@ -164,6 +207,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         if (nlhs > 5) plhs[5] = mxCreateDoubleScalar(st.t_solve_ms * 1e-3);
     } else if (cmd == "destroy") {
         fail_if(cpk_destroy(as_handle(prhs[1])));
+        auto it = g_ops.find(as_handle(prhs[1]));
+        if (it != g_ops.end()) { mxDestroyArray(it->second); g_ops.erase(it); }
     } else {
         mexErrMsgIdAndTxt("cpk_b200:arg", "unknown command %s", cmd.c_str());
     }

@@ -4,8 +4,9 @@ function [x, stats, flag] = reg_cpkrylov_gpu(method, b, A, B, C, G, opts)
 % cpk_b200_mex / libcpk_b200.so.  Only the factorization stays on the host
 % (untimed setup, stats.ptime), exactly where the reference calls ldl (opLDL2.m:82).
 %
-% Limitation: A must be an explicit sparse matrix (the reference also accepts a
-% Spot operator, reg_cpkrylov.m:40; use opLDL2gpu + the original kernels for that).
+% A may be a matrix or a linear operator (reg_cpkrylov.m:40): a Spot operator or a function
+% handle is evaluated on the host, through mexCallMATLAB, from inside the one device launch
+% (only v and A*v cross the bus per iteration); B, C and G must be explicit matrices.
     if (nargin < 6)
         error('reg_cpkrylov: not enough inputs');                 % reg_cpkrylov.m:122-125
     end
@@ -19,7 +20,11 @@ function [x, stats, flag] = reg_cpkrylov_gpu(method, b, A, B, C, G, opts)
     K = [G B'; B -C];
     [L, D, P] = ldl(K);                                           % opLDL2.m:81-82 (HSL MA57)
     hM = cpk_b200_mex('ldl2_create', sparse(G), sparse(B), sparse(-C), L, D, sparse(P));
-    hS = cpk_b200_mex('system_create', sparse(A), sparse(C), hM);
+    if isnumeric(A)
+        hS = cpk_b200_mex('system_create', sparse(A), sparse(C), hM);
+    else
+        hS = cpk_b200_mex('system_create_op', n, A, sparse(C), hM);
+    end
     ptime = toc(tstartp);
     cleanup = onCleanup(@() cpk_b200_mex('destroy', hS));
 

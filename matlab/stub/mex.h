@@ -32,6 +32,10 @@ mxArray *mxCreateDoubleScalar(double v);
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray *mxCreateLogicalScalar(bool v);
 void mxDestroyArray(mxArray *a);
+mxArray *mxDuplicateArray(const mxArray *a);
+void mexMakeArrayPersistent(mxArray *a);
+bool mxIsClass(const mxArray *a, const char *name);
+int mexCallMATLAB(int nlhs, mxArray *plhs[], int nrhs, mxArray *prhs[], const char *fn);
 void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...);
 int mexAtExit(void (*fn)(void));
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);

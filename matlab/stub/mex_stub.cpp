@@ -55,6 +55,23 @@ mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity)
 mxArray *mxCreateDoubleScalar(double v) { mxArray *a = mxCreateDoubleMatrix(1, 1, mxREAL); a->pr[0] = v; return a; }
 mxArray *mxCreateLogicalScalar(bool v) { mxArray *a = mxCreateDoubleScalar(v ? 1.0 : 0.0); a->is_logical = true; return a; }
 void mxDestroyArray(mxArray *a) { delete a; }
+mxArray *mxDuplicateArray(const mxArray *a) { return new mxArray_tag(*a); }
+void mexMakeArrayPersistent(mxArray *) {}
+bool mxIsClass(const mxArray *a, const char *name) { return !std::strcmp(name, "double") && !a->is_char && !a->is_logical; }
+static int g_callbacks = 0;
+// the toy interpreter knows ONE function: mtimes(sparse matrix, dense vector)
+int mexCallMATLAB(int nlhs, mxArray *plhs[], int nrhs, mxArray *prhs[], const char *fn)
+{
+    if (std::strcmp(fn, "mtimes") || nlhs != 1 || nrhs != 2 || !prhs[0]->sparse || prhs[1]->sparse || prhs[1]->m != prhs[0]->n) return 1;
+    const mxArray *A = prhs[0], *v = prhs[1];
+    mxArray *u = mxCreateDoubleMatrix(A->m, 1, mxREAL);
+    for (size_t j = 0; j < A->n; ++j)
+        for (mwIndex k = A->jc[j]; k < A->jc[j + 1]; ++k) u->pr[A->ir[k]] += A->pr[k] * v->pr[j];
+    plhs[0] = u;
+    ++g_callbacks;
+    return 0;
+}
+int stub_callbacks(void) { return g_callbacks; }
 void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...)
 {
     char buf[2048];

@@ -135,4 +135,14 @@ def test_gateway_reg_solve_cpsymmlq_three_histories():
     assert np.allclose(hist[:, 2], sr["qrresidHistory"], rtol=1e-12)
     assert tdev[0, 0] > 0
     mex.call(0, "destroy", float(hS[0, 0]))
+    # the same solve with A as an operator (reg_cpkrylov.m:40): the gateway evaluates A*v through
+    # mexCallMATLAB (the toy interpreter multiplies by the sparse matrix) while the kernel is resident
+    mex.L.stub_callbacks.restype = ct.c_int
+    c0 = mex.L.stub_callbacks()
+    hS2, = mex.call(1, "system_create_op", float(s["n"]), s["Q"], s["C"], float(hM[0, 0]))
+    x2, niters2, solved2 = mex.call(3, "reg_solve", float(hS2[0, 0]), 3.0, s["rhs"], ov, [float(s["n"]), float(s["m"])])
+    assert int(niters2[0, 0]) == sr["niters"] and bool(solved2[0, 0]) == fr["solved"]
+    assert mex.L.stub_callbacks() - c0 >= sr["niters"]
+    assert np.allclose(x2.ravel(), xr, rtol=1e-7, atol=0)          # cpsymmlq amplifies rounding (profiles/r2_parity_table.jsonl)
+    mex.call(0, "destroy", float(hS2[0, 0]))
     mex.call(0, "destroy", float(hM[0, 0]))
