@@ -450,15 +450,27 @@ static bool use_grid(int N)
 // i.e. one CTA ~ 20 + 0.016 N (+ 1.2 per level when the compact walk is needed), grid ~ 55 for sweeps
 // the tail inversion flattens (<= 48 levels here) and ~ 50 + 5 per level otherwise.
 // Batches keep the size rule (use_grid): there one SM per system is the point.
-static bool model_prefers_grid(int N, int levels, bool compact_fits)
+// Cost model of one iteration (two LDL' solves), us, fitted to measurements on the example systems and the
+// kkt_lap3d family (`scripts/compact_probe.py`, `scripts/team_crossover.py`):
+//   `eff`   depth of the two sweeps after level merging (what the global-memory walks pay per level),
+//   `raw`   depth of the factor itself (what the compact walk pays: its stream is not merged),
+//   `items` length of the merged item list (one SM walks it at ~0.05 us per item).
+// cvxqp1 (N = 5 500, 70+70 -> 4+5 levels, 2 886 items): one CTA level walk 378, compact walk 202, grid 138;
+// cvxqp2 (N = 725, 10+10 -> 1+1 levels, 66 items): one CTA level walk 47, compact walk 54, grid 80.
+static double model_cta_level(int N, int eff, int items) { return 20.0 + 0.016 * N + 2.0 * (0.05 * items + 2.3 * std::max(eff - 2, 0)); }
+static double model_cta_compact(int N, int raw) { return 20.0 + 0.016 * N + 1.2 * raw; }
+// the walk of a ONE-CTA team (single small system, or one system of a batch)
+static bool model_prefers_compact(int eff, int raw, int items) { return model_cta_compact(0, raw) < model_cta_level(0, eff, items); }
+// the team of a SINGLE-system launch (batches keep the size rule, use_grid: there one SM per system is the point)
+static bool model_prefers_grid(int N, int eff, int raw, int items, bool compact_allowed)
 {
     if (const char *e = getenv("CPK_TEAM")) {
         if (!strcmp(e, "grid")) return true;
         if (!strcmp(e, "cta")) return false;
     }
     if (use_grid(N)) return true;
-    const double cta = 20.0 + 0.016 * N + ((levels > 24 && compact_fits) ? 1.2 * levels : (levels > 24 ? 4.6 * levels : 0.0));
-    const double grid = levels <= 48 ? 55.0 : 50.0 + 5.0 * levels;
+    const double cta = std::min(model_cta_level(N, eff, items), compact_allowed ? model_cta_compact(N, raw) : 1e300);
+    const double grid = 55.0 + 5.0 * std::max(eff - 2, 0);
     return grid < cta;
 }
 static bool team_is_grid(const Ldl2 *M);
@@ -810,30 +822,28 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         fused[i] = hasR[i] && !hasC[i] && partner[i] < 0;       // y_i = w_i/d_i inside the forward item
     }
     if (getenv("CPK_LDL_NO_SHORTCUTS")) { std::fill(triv.begin(), triv.end(), 0); std::fill(fused.begin(), fused.end(), 0); }
-    // Depth reduction: the last levels of a sweep hold few rows but cost one
-    // cross-SM hop each.  Rows of levels >= cut are rewritten by substituting
-    // their in-tail dependencies (an explicit inverse of the small unit-
-    // triangular tail block, built row by row), so the whole tail becomes ONE
-    // level that depends only on earlier levels and on the input vector.
-    // Skipped when the substitution would fill in or grow too much.
-    // a system that will walk the compact stream keeps the global sweep only as a fallback
-    // (a solver scratch too large for the stream's shared memory): no tail inversion for it,
-    // which is most of the host-side set-up time of a small system
+    // Depth reduction ("level merging"): a level costs one cross-SM hop (a team barrier, or a tagged
+    // round trip in the sync-free walk) whatever its size, and the deep part of a filled factor is a
+    // long chain of levels of a few rows each (k=6 windowed stress system: 578 of 629 levels hold
+    // fewer than 32 rows).  Consecutive levels are therefore merged into GROUPS: the rows of a group
+    // are rewritten by substituting their in-group dependencies (an explicit inverse of the group's
+    // small unit-triangular block, built row by row), so the whole group becomes ONE level that
+    // depends only on earlier groups and on the input vector.  Groups grow greedily, level by level,
+    // while the substitution stays cheap and tame: entries of the group <= tail_fill_max x the
+    // original ones, coefficients <= 10^3 x the scale of L (L'/D), rows <= max(tail_len_max, 3 x their
+    // original length).  A fill-free forest-shaped factor (cfg 3 / cfg 4: 19+19 levels) collapses
+    // to 1+1 levels; the stress factor to a few dozen.  A level with a 2x2 pivot closes the group.
+    // A system that will walk the compact stream keeps the global sweep only as a fallback
+    // (a solver scratch too large for the stream's shared memory): no merging for it,
+    // which is most of the host-side set-up time of a small system.
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
-    static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 128LL); }();
-    auto choose_cut = [&](const std::vector<int> &lev, const std::vector<char> &skip, int &maxlev) {
-        std::vector<long long> cnt;
-        for (int i = 0; i < N; ++i) if (!skip[i]) { if ((size_t)lev[i] >= cnt.size()) cnt.resize(lev[i] + 1, 0); cnt[lev[i]]++; }
-        maxlev = (int)cnt.size() - 1;
-        long long tail = 0;
-        int cut = maxlev + 1;
-        static const int lmin = (getenv("CPK_LDL_CUT0") && atoi(getenv("CPK_LDL_CUT0")) == 0) ? 1 : 0;
-        for (int l = maxlev; l >= lmin; --l) { if (tail + cnt[l] > tail_rows_max) break; tail += cnt[l]; cut = l; }
-        return cut;
-    };
+    static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 256LL); }();
+    static const int merge_lmin = (getenv("CPK_LDL_CUT0") && atoi(getenv("CPK_LDL_CUT0")) == 0) ? 1 : 0;
+    const bool merging = !getenv("CPK_LDL_NO_TAIL") && !compact_walk;
     auto add_to = [](std::vector<std::pair<int, double>> &acc, int code, double v) { acc.emplace_back(code, v); };
     auto compress = [](EncRow &r) {         // merge equal codes, keep first-appearance order
+        if (r.size() < 2) return;
         std::vector<std::pair<int, double>> out;
         std::unordered_map<int, size_t> pos;
         for (auto &x : r) {
@@ -845,6 +855,78 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
     };
     double maxL = 1.0;
     for (double v : Lrows.val) maxL = std::max(maxL, std::fabs(v));
+    // The greedy grouping, shared by the two sweeps.  `lev` (levels of the rows not in `skip`) is
+    // rewritten to group numbers; `expd` receives the substituted rows of every group of more than
+    // one level.  expand(t, grp, gid, acc, orig): encoded dependency list of row t with the
+    // dependencies inside group gid substituted (reads expd of rows handled before), `orig` +=
+    // its original entry count.  scale(t): what the coefficients of row t are judged against.
+    auto merge_levels = [&](std::vector<int> &lev, const std::vector<char> &skip, bool descending, std::unordered_map<int, EncRow> &expd,
+                            auto &&expand, auto &&blocker, auto &&scale_of, auto &&orig_len) {
+        int maxlev = -1;
+        for (int i = 0; i < N; ++i) if (!skip[i]) maxlev = std::max(maxlev, lev[i]);
+        if (maxlev < 0) return;
+        std::vector<std::vector<int>> by_lev((size_t)maxlev + 1);
+        if (descending) { for (int i = N - 1; i >= 0; --i) if (!skip[i]) by_lev[lev[i]].push_back(i); }
+        else { for (int i = 0; i < N; ++i) if (!skip[i]) by_lev[lev[i]].push_back(i); }
+        std::vector<int> grp((size_t)N, -1);
+        int gid = -1, g_levels = 0;
+        long long g_orig = 0, g_fill = 0, g_nrows = 0;
+        double g_scale = maxL;
+        bool g_closed = true;
+        std::vector<int> g_rows;
+        auto close_group = [&] {
+            if (g_levels == 1) for (int t : g_rows) expd.erase(t);      // a lone level keeps its original rows
+            g_rows.clear();
+        };
+        std::unordered_map<int, EncRow> cand;
+        for (int l = 0; l <= maxlev; ++l) {
+            const std::vector<int> &rows = by_lev[l];
+            bool blk = false;
+            for (int t : rows) if (blocker(t)) { blk = true; break; }
+            bool joined = false;
+            if (merging && !g_closed && !blk && l >= merge_lmin + 1 && g_nrows + (long long)rows.size() <= tail_rows_max) {
+                cand.clear();
+                long long lorig = 0, lfill = 0;
+                double growth = 0.0, sc = g_scale;
+                bool ok = true;
+                for (int t : rows) {
+                    EncRow acc;
+                    expand(t, grp, gid, acc, lorig);
+                    compress(acc);
+                    lfill += (long long)acc.size();
+                    for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
+                    sc = std::max(sc, scale_of(t));
+                    if (acc.size() > std::max(tail_len_max, (size_t)3 * (size_t)orig_len(t)) ||
+                        (double)(g_fill + lfill) > tail_fill_max * (double)std::max<long long>(g_orig + lorig, 1) + 1024.0) { ok = false; break; }
+                    cand[t] = std::move(acc);
+                }
+                if (ok && !(growth <= 1e3 * sc)) ok = false;
+                if (ok) {
+                    for (auto &kv : cand) { expd[kv.first] = std::move(kv.second); grp[kv.first] = gid; g_rows.push_back(kv.first); }
+                    g_orig += lorig; g_fill += lfill; g_nrows += (long long)rows.size(); g_scale = sc; ++g_levels;
+                    joined = true;
+                }
+            }
+            if (!joined) {
+                close_group();
+                ++gid; g_levels = 1; g_orig = 0; g_fill = 0; g_nrows = (long long)rows.size(); g_scale = maxL;
+                g_closed = blk || !merging || l < merge_lmin;
+                for (int t : rows) {
+                    grp[t] = gid;
+                    if (!g_closed) {
+                        EncRow acc;
+                        expand(t, grp, -2, acc, g_orig);        // no in-group dependency yet: the encoded original row
+                        g_fill += (long long)acc.size();
+                        g_scale = std::max(g_scale, scale_of(t));
+                        expd[t] = std::move(acc);
+                        g_rows.push_back(t);
+                    }
+                }
+            }
+        }
+        close_group();
+        for (int i = 0; i < N; ++i) if (!skip[i]) lev[i] = grp[i];
+    };
     std::vector<int> levf(N, 0), levb(N, 0);
     std::unordered_map<int, EncRow> tailf, tailb;
     std::vector<SweepRow> rowsF, rowsB;
@@ -856,34 +938,21 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
             for (int64_t k = Lrows.ptr[i]; k < Lrows.ptr[i + 1]; ++k) { const int jx = Lrows.col[k]; if (!triv[jx]) lv = std::max(lv, levf[jx] + 1); }
             levf[i] = lv;
         }
-        int maxlev = 0;
-        int cut = choose_cut(levf, triv, maxlev);
-        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL") && !compact_walk; ++attempt, cut += (maxlev - cut + 1) / 2) {
-            long long orig = 0, fill = 0;
-            double growth = 0.0;
-            bool okinv = true;
-            for (int t = 0; t < N && okinv; ++t) {
-                if (triv[t] || levf[t] < cut) continue;
-                EncRow acc;
+        merge_levels(levf, triv, false, tailf,
+            [&](int t, const std::vector<int> &grp, int gid, EncRow &acc, long long &orig) {
                 for (int64_t k = Lrows.ptr[t]; k < Lrows.ptr[t + 1]; ++k) {
                     const int jx = Lrows.col[k]; const double a = Lrows.val[k];
                     ++orig;
                     if (triv[jx]) add_to(acc, (int)(-(p[jx]) - 2), a);
-                    else if (levf[jx] >= cut) {
+                    else if (grp[jx] == gid) {
                         add_to(acc, (int)(-(p[jx]) - 2), a);            // the z_j part of w_j
                         for (auto &x : tailf[jx]) add_to(acc, x.first, -a * x.second);
                     } else add_to(acc, jx, a);
                 }
-                compress(acc);
-                fill += (long long)acc.size();
-                for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
-                if (fill > tail_fill_max * std::max<long long>(orig, 1) + 1024 || growth > 1e3 * maxL || acc.size() > tail_len_max) okinv = false;
-                tailf[t] = std::move(acc);
-            }
-            if (!okinv) { tailf.clear(); continue; }
-            for (auto &kv : tailf) levf[kv.first] = cut;
-            break;
-        }
+            },
+            [&](int) { return false; },
+            [&](int) { return maxL; },
+            [&](int t) { return Lrows.len(t); });
         for (int i = 0; i < N; ++i) {
             if (triv[i]) continue;
             auto it = tailf.find(i);
@@ -900,41 +969,22 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
             for (int64_t k = Lcols.ptr[i]; k < Lcols.ptr[i + 1]; ++k) { const int r = Lcols.col[k]; if (!fused[r]) lv = std::max(lv, levb[r] + 1); }
             levb[i] = lv;
         }
-        int maxlev = 0;
-        int cut = choose_cut(levb, fused, maxlev);
-        for (int attempt = 0; attempt < 5 && cut < maxlev && !getenv("CPK_LDL_NO_TAIL") && !compact_walk; ++attempt, cut += (maxlev - cut + 1) / 2) {
-            bool tail_has_2x2 = false;
-            for (int i = 0; i < N; ++i) if (!fused[i] && levb[i] >= cut && partner[i] >= 0) tail_has_2x2 = true;
-            if (tail_has_2x2) continue;
-            long long orig = 0, fill = 0;
-            double growth = 0.0;
-            bool okinv = true;
-            for (int t = N - 1; t >= 0 && okinv; --t) {
-                if (fused[t] || levb[t] < cut) continue;
-                EncRow acc;
+        merge_levels(levb, fused, true, tailb,
+            [&](int t, const std::vector<int> &grp, int gid, EncRow &acc, long long &orig) {
                 for (int64_t k = Lcols.ptr[t]; k < Lcols.ptr[t + 1]; ++k) {
                     const int r = Lcols.col[k]; const double a = Lcols.val[k];
                     ++orig;
-                    if (!fused[r] && levb[r] >= cut) {
-                        // y_r = w_r/d_r - sum(tail deps of r):  a*y_r
+                    if (!fused[r] && grp[r] == gid) {
+                        // y_r = w_r/d_r - sum(in-group deps of r):  a*y_r
                         add_to(acc, triv[r] ? (int)(-(p[r]) - 2) : N + r, a / d[r]);
                         for (auto &x : tailb[r]) add_to(acc, x.first, -a * x.second);
                     } else add_to(acc, r, a);
                 }
-                compress(acc);
-                fill += (long long)acc.size();
-                for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
-                if (fill > tail_fill_max * std::max<long long>(orig, 1) + 1024 || acc.size() > tail_len_max) okinv = false;
-                tailb[t] = std::move(acc);
-            }
+            },
+            [&](int t) { return partner[t] >= 0; },
             // growth is judged against the scale of L'/D entries actually present
-            double scale = maxL;
-            for (auto &kv : tailb) scale = std::max(scale, maxL / std::max(std::fabs(d[kv.first]), 1e-300));
-            if (growth > 1e3 * scale) okinv = false;
-            if (!okinv) { tailb.clear(); continue; }
-            for (auto &kv : tailb) levb[kv.first] = cut;
-            break;
-        }
+            [&](int t) { return std::max(maxL, maxL / std::max(std::fabs(d[t]), 1e-300)); },
+            [&](int t) { return Lcols.len(t); });
         for (int i = 0; i < N; ++i) {
             if (fused[i]) continue;
             auto it = tailb.find(i);
@@ -1063,15 +1113,20 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
     HCsr &Lrows = HL.Lrows, &Lcols = HL.Lcols;
     std::vector<int> &lf = HL.lf, &lb = HL.lb;
     const int nlf = HL.nlf, nlb = HL.nlb;
-    // ---- the sweeps: item list and / or row-class form
+    // ---- the sweeps: item list and / or row-class form.  Level merging runs first (it is what
+    // decides how deep the sweeps really are); team and walk are chosen from the EFFECTIVE depth.
     const char *cenv = getenv("CPK_LDL_COMPACT");
     const bool compact_fits = !use_grid(N) && cw_smem_bytes(N, n2 == 0) <= (size_t)dc->max_dsm;
-    const bool prefer_grid = !g_force_compact && model_prefers_grid(N, nlf + nlb, compact_fits && !(cenv && atoi(cenv) == 0));
-    const bool compact_walk = g_force_compact ||
-                              (compact_fits && !prefer_grid && !(cenv && atoi(cenv) == 0) && (nlf + nlb > 24 || (cenv && atoi(cenv) == 1)));
     SweepBuild SB;
-    rc = build_sweeps(HL, N, compact_walk, g_grid_warps_hint, &SB);
+    rc = build_sweeps(HL, N, g_force_compact, g_grid_warps_hint, &SB);
     if (rc) return rc;
+    const int eff_levels = SB.W.lev_f_eff + SB.W.lev_b_eff;
+    const bool compact_allowed = compact_fits && !(cenv && atoi(cenv) == 0);
+    const bool prefer_grid = !g_force_compact && model_prefers_grid(N, eff_levels, nlf + nlb, SB.W.nitems, compact_allowed);
+    // the compact stream is built whenever a one-CTA team would want it -- also for an operator whose
+    // single-system launches go to the grid: the same operator may be one system of a batch
+    const bool compact_walk = g_force_compact ||
+                              (compact_allowed && (model_prefers_compact(eff_levels, nlf + nlb, SB.W.nitems) || (cenv && atoi(cenv) == 1)));
     HSweep &W = SB.W;
     HRc &RC = SB.RC;
     const bool have_rc = SB.have_rc, want_items = SB.want_items, walk_deep = SB.walk_deep;
@@ -1254,6 +1309,42 @@ extern "C" int cpk_debug_rc(const cpk_csc *A, const cpk_csc *L, const cpk_csc *D
         if (lptr) std::copy(R->lptr.begin(), R->lptr.end(), lptr);
         if (lcol) std::copy(R->lcol.begin(), R->lcol.end(), lcol);
         if (lval) std::copy(R->lval.begin(), R->lval.end(), lval);
+        return (int)CPK_OK;
+    });
+}
+
+// debug / test hook (no device needed): the item list of the two sweeps (DevSweep) as build_sweeps
+// compiles it for a grid team -- trivial / fused rows, level merging, warp-rows -- so that a numpy
+// walk can check it against a direct solve.  sizes = {nitems, nfwd, nlev, entries, effective forward
+// levels, effective backward levels, rows rewritten by the merging (fwd), (bwd)}; the arrays may be
+// null (sizes only).
+extern "C" int cpk_debug_sweep(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int64_t *sizes, int32_t *levptr, int32_t *sptr,
+                               int32_t *col, double *val, int32_t *rid, int32_t *pidx, int32_t *flags, double *d, int32_t *partner,
+                               double *e, double *dp)
+{
+    return guarded([&]() -> int {
+        if (!csc_ok(L) || !csc_ok(D) || !perm || !sizes) return fail(CPK_ERR_ARG, "cpk_debug_sweep: bad argument");
+        const int N = (int)L->nrows;
+        HostLdl HL;
+        int rc = parse_ldl(L, D, perm, N, &HL);
+        if (rc) return rc;
+        SweepBuild SB;
+        rc = build_sweeps(HL, N, false, 148 * kWarpsPerCta, &SB);
+        if (rc) return rc;
+        const HSweep &W = SB.W;
+        sizes[0] = W.nitems; sizes[1] = W.nfwd; sizes[2] = (int64_t)W.levptr.size(); sizes[3] = (int64_t)W.col.size();
+        sizes[4] = W.lev_f_eff; sizes[5] = W.lev_b_eff; sizes[6] = W.tail_f; sizes[7] = W.tail_b;
+        if (levptr) { std::copy(W.levptr.begin(), W.levptr.end(), levptr); levptr[W.levptr.size()] = W.nitems; }
+        if (sptr) std::copy(W.sptr.begin(), W.sptr.end(), sptr);
+        if (col) std::copy(W.col.begin(), W.col.end(), col);
+        if (val) std::copy(W.val.begin(), W.val.end(), val);
+        if (rid) std::copy(W.rid.begin(), W.rid.end(), rid);
+        if (pidx) std::copy(W.pidx.begin(), W.pidx.end(), pidx);
+        if (flags) std::copy(W.flags.begin(), W.flags.end(), flags);
+        if (d) std::copy(W.d.begin(), W.d.end(), d);
+        if (partner) std::copy(W.partner.begin(), W.partner.end(), partner);
+        if (e) std::copy(W.e.begin(), W.e.end(), e);
+        if (dp) std::copy(W.dp.begin(), W.dp.end(), dp);
         return (int)CPK_OK;
     });
 }

@@ -57,7 +57,7 @@ def run(env_extra):
     for line in p.stdout.splitlines():
         if line.startswith("RESULT "):
             res = json.loads(line[7:])
-        elif "[cpk]" in line and "compact" in line:
+        elif "[cpk]" in line and ("compact" in line or "LDL sweep" in line):
             print("   ", line.strip())
     if res is None:
         print(p.stdout[-3000:])
@@ -66,9 +66,12 @@ def run(env_extra):
 
 if __name__ == "__main__":
     allres = {}
-    configs = (("compact", {"CPK_VERBOSE": "1"}), ("level-walk", {"CPK_LDL_COMPACT": "0"}), ("compact-again", {}))
+    configs = (("default", {"CPK_VERBOSE": "1"}), ("cta level-walk", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "0"}),
+               ("cta compact", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1"}), ("grid", {"CPK_TEAM": "grid"}),
+               ("grid level barriers", {"CPK_TEAM": "grid", "CPK_LDL_SYNCFREE": "0"}),
+               ("cta level-walk, no merging", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "0", "CPK_LDL_NO_TAIL": "1"}))
     if "--quick" in sys.argv:
-        configs = (("compact", {"CPK_VERBOSE": "1"}),)
+        configs = (("default", {"CPK_VERBOSE": "1"}),)
     for label, env in configs:
         r = run(env)
         allres[label] = r

@@ -1,8 +1,10 @@
-set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "walk_variants or opldl2 or full_size_properties or stress" 2>&1 | tail -15 > gpurun_out/r2_pytest12.log; cat gpurun_out/r2_pytest12.log
-export LIBS=b200
-timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/items/' | tee gpurun_out/r2_ab12.log
-CPK_LDL_RC=1 timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/rc-staged/' | tee -a gpurun_out/r2_ab12.log
-CPK_LDL_RC=1 CPK_RESID_RC=1 timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/rc+resid-staged/' | tee -a gpurun_out/r2_ab12.log
-CPK_LDL_RC=1 CPK_RESID_RC=1 CPK_RC_STAGE=0 timeout 600 scripts/ab_r2.sh 2>&1 | sed 's/^b200/rc+resid-unstaged/' | tee -a gpurun_out/r2_ab12.log
+timeout 900 python scripts/compact_probe.py --quick 2>&1 | tee gpurun_out/r2_compact18.log | grep -v "^ " | cut -c1-1200
+python bench.py --workload ipm_batch --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_batch18.json
+out=gpurun_out/r2_stress18.log; : > $out
+run() { env "$@" timeout 300 python scripts/stress_env_probe.py 40 "$*" 2>&1 | tail -1 | tee -a $out; }
+run A=0
+run CPK_LDL_TAIL_MAXLEN=384
+run CPK_LDL_TAIL_FILL=10
+run CPK_LDL_TAIL_FILL=10 CPK_LDL_TAIL_MAXLEN=384
+run CPK_LDL_TAIL_FILL=4

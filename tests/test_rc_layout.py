@@ -207,12 +207,14 @@ def test_rc_sweeps_cvxqp2_superlu():
 
 
 def test_rc_sweeps_cvxqp1_superlu_deep():
-    """69+69 levels: too deep for the row-class form on the device tables (kRcMaxLev = 48):
-    the builder must say so (the item list / compact walk serve it)."""
+    """69+69 levels in the factor: too deep for the row-class tables (kRcMaxLev = 48) as they stand,
+    but level merging (build_sweeps) brings the sweeps down to a dozen groups, so the row-class
+    form is built after all and must give the direct solve."""
     s = load_system("cvxqp1_m")
     L, d, e, perm = load_factors("cvxqp1_m", "superlu")
     R = _rc(L=L, d=d, perm=perm)
-    assert R["have"] == 0
+    assert R["have"] == 1 and R["nlev"] <= 48
+    _check_sweeps(L, d, perm, seed=3)
 
 
 @pytest.mark.parametrize("g,k,window", [(8, 2, 0), (10, 2, 0), (8, 6, 16)])
