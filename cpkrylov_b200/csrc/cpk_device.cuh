@@ -165,7 +165,12 @@ struct DevSweep {
     const int    *sptr;     // [nitems+1]
     const int    *col;
     const double *val;
-    const int    *rid;      // [nitems*32] LDL row id, -1 = idle lane
+    // Row data of the items, one slot per (item, lane) -- `mptr` == nullptr: slot = item*32 + lane.
+    // A sweep made mostly of warp-rows (merged levels of a filled factor) stores ONE slot for such
+    // an item instead of 32 (31 of them idle lanes): mptr [nitems+1] is then the first slot of every
+    // item, and an item with a single slot is read by all its lanes (item_slot below).
+    const int    *mptr;
+    const int    *rid;      // [slots] LDL row id, -1 = idle lane
     const int    *pidx;     // [nitems*32] index into the user vector (perm[rid])
     const int    *flags;    // [nitems*32] F_* bits
     const double *d;        // [nitems*32] own diagonal entry of D
@@ -173,6 +178,12 @@ struct DevSweep {
     const double *e;        // off-diagonal of the 2x2 block
     const double *dp;       // partner's diagonal entry
 };
+__device__ __forceinline__ int item_slot(const DevSweep &S, int t, int lane)
+{
+    if (S.mptr == nullptr) return t * 32 + lane;
+    const int mb = __ldg(&S.mptr[t]);
+    return (__ldg(&S.mptr[t + 1]) - mb == 1) ? mb : mb + lane;
+}
 
 // One-CTA walk of the LDL' solve ("compact walk", small systems): the sweep values
 // w and y live in SHARED memory and the factor is streamed through a shared-memory

@@ -213,6 +213,31 @@ static cudaError_t upload_sweep(DevArena &ar, const HSweep &h, DevSweep &d)
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    d.mptr = nullptr;
+    static const bool no_compact_meta = getenv("CPK_LDL_DENSE_META") != nullptr;
+    if (h.nitems >= 4096 && h.n_warprow * 4 > (int64_t)h.nitems && !no_compact_meta) {
+        // mostly warp-rows: one slot of row data per warp-row item instead of 32 (see DevSweep::mptr)
+        std::vector<int> mptr((size_t)h.nitems + 1, 0), rid, pidx, flags, partner;
+        std::vector<double> dd, ee, dp;
+        for (int t = 0; t < h.nitems; ++t) {
+            const size_t b = (size_t)t * 32;
+            const int cnt = (h.flags[b] & F_WARPROW) ? 1 : 32;
+            for (int l = 0; l < cnt; ++l) {
+                rid.push_back(h.rid[b + l]); pidx.push_back(h.pidx[b + l]); flags.push_back(h.flags[b + l]); partner.push_back(h.partner[b + l]);
+                dd.push_back(h.d[b + l]); ee.push_back(h.e[b + l]); dp.push_back(h.dp[b + l]);
+            }
+            mptr[t + 1] = (int)rid.size();
+        }
+        if ((e = ar.upload(&d.mptr, mptr)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.rid, rid)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.pidx, pidx)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.flags, flags)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.d, dd)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.partner, partner)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.e, ee)) != cudaSuccess) return e;
+        if ((e = ar.upload(&d.dp, dp)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
     if ((e = ar.upload(&d.rid, h.rid)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.pidx, h.pidx)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.flags, h.flags)) != cudaSuccess) return e;

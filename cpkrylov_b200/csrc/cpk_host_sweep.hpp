@@ -87,9 +87,26 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
     // order them by their index in the user vector, so that the P' gather and the
     // P scatter of consecutive lanes touch consecutive addresses
     for (auto &rw : rows) W.max_len = std::max<int64_t>(W.max_len, rw.len);
+    // Rows longer than the level's threshold become warp-rows (one warp per row: the shortest chain
+    // for a level of few rows, where latency is all that counts).  A WIDE level of a large system
+    // (several rows per warp of the grid) is bound by item throughput instead -- a warp-row of 10..40
+    // entries keeps a whole warp busy for the same dependent round trips as a lane item of 32 rows
+    // -- so a level with MANY such rows (several per warp of the grid: merged levels of a filled
+    // factor hold hundreds of thousands) keeps rows of up to 32 entries as lane items.
+    static const int wide_thr = [] { const char *e = getenv("CPK_LDL_WIDE_ROW"); return e ? atoi(e) : 32; }();
+    std::vector<long long> lvl_mid;        // rows of kLongRow+1 .. wide_thr entries per level
+    for (auto &rw : rows) {
+        if ((size_t)rw.level >= lvl_mid.size()) lvl_mid.resize((size_t)rw.level + 1, 0);
+        if (rw.len > kLongRow && rw.len <= wide_thr) lvl_mid[rw.level]++;
+    }
+    auto long_thr = [&](int level) {
+        if ((int)perm.size() <= 24576) return kLongRow;
+        return lvl_mid[level] >= 4LL * grid_warps ? std::max(wide_thr, kLongRow) : kLongRow;
+    };
     std::stable_sort(rows.begin(), rows.end(), [&](const SweepRow &a, const SweepRow &b) {
         if (a.level != b.level) return a.level < b.level;
-        const int la = std::min(a.len, kLongRow + 1), lb = std::min(b.len, kLongRow + 1);
+        const int thr = long_thr(a.level);
+        const int la = std::min(a.len, thr + 1), lb = std::min(b.len, thr + 1);
         if (la != lb) return la > lb;
         return perm[a.row] < perm[b.row];
     });
@@ -100,8 +117,9 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
     while (i0 < rows.size()) {
         const int lev = rows[i0].level;
         const int first_item = W.nitems;
+        const int thr = long_thr(lev);
         while (i0 < rows.size() && rows[i0].level == lev) {
-            if (rows[i0].len > kLongRow) {
+            if (rows[i0].len > thr) {
                 // one long row = one item, entries spread over the 32 lanes
                 const int r = rows[i0].row;
                 const EncRow er = entries(r);
@@ -126,7 +144,7 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
                 continue;
             }
             size_t i1 = i0;
-            while (i1 < rows.size() && i1 - i0 < 32 && rows[i1].level == lev && rows[i1].len <= kLongRow) ++i1;
+            while (i1 < rows.size() && i1 - i0 < 32 && rows[i1].level == lev && rows[i1].len <= thr) ++i1;
             int width = 0;
             for (size_t t = i0; t < i1; ++t) width = std::max(width, rows[t].len);
             const size_t base = W.col.size();

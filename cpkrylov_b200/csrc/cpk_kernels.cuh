@@ -299,7 +299,7 @@ __device__ __forceinline__ void item_load(const DevSweep &S, int t, int lane, It
 {
     m.beg = __ldg(&S.sptr[t]);
     m.end = __ldg(&S.sptr[t + 1]);
-    m.slot = t * 32 + lane;
+    m.slot = item_slot(S, t, lane);
     m.rid = __ldg(&S.rid[m.slot]);
     m.pidx = __ldg(&S.pidx[m.slot]);
     m.flags = __ldg(&S.flags[m.slot]);
@@ -484,7 +484,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                 if (q < nb) {
                     beg[q] = __ldg(&S.sptr[t + q]);
                     wid[q] = __ldg(&S.sptr[t + q + 1]) - beg[q];
-                    const int slot = (t + q) * 32 + lane;
+                    const int slot = item_slot(S, t + q, lane);
                     rid[q] = __ldg(&S.rid[slot]); pidx[q] = __ldg(&S.pidx[slot]);
                     flg[q] = __ldg(&S.flags[slot]); dd[q] = __ldg(&S.d[slot]);
                 } else { beg[q] = 0; wid[q] = 0; rid[q] = -1; pidx[q] = 0; flg[q] = 0; dd[q] = 1.0; }
