@@ -263,27 +263,25 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def run_batch(args, rank, local_rank, world):
+def batch_measure(args, rank, local_rank, world, steps, warmup, total=None, per_gpu=0, g=0):
     """BASELINE cfg 5: a batch of independent IPM-like KKT systems (pattern of the
     reference's cvxqp1 example), block-partitioned over the ranks; every rank solves
-    its share in ONE launch (one CTA per system).  Not the headline line -- run with
-    --workload ipm_batch."""
+    its share in ONE launch (one CTA per system).  Timed end to end through the host-pointer
+    batch ABI (H2D right-hand sides, D2H solutions inside the timed region), barrier on both
+    sides, max over ranks.  The process group (world > 1) must exist.  Returns the line on rank 0."""
     import torch
     import torch.distributed as dist
     from cpkrylov_b200 import synth
     from cpkrylov_b200.batch import BatchSolver, partition
     from cpkrylov_b200.ldl import ldl_superlu
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    total = args.batch_per_gpu * world if args.batch_per_gpu > 0 else args.batch
+    total = per_gpu * world if per_gpu > 0 else (total or 256)
     lo, hi = partition(total, world, rank)
     opts = dict(atol=1e-6, rtol=1e-6, itmax=500, residual_update=True, nitref=1, force_itref=True)
     t0 = time.perf_counter()
-    if args.g > 0:
+    if g > 0:
         # larger variant (SURVEY section 8d): cfg-3 pattern on a g^3 grid; systems beyond the one-CTA
         # limit share cooperative launches as sub-teams of the grid
-        systems = [synth.ipm_batch_lap3d(args.g, j) for j in range(lo, hi)]
+        systems = [synth.ipm_batch_lap3d(g, j) for j in range(lo, hi)]
         base = dict(n=systems[0]["n"], m=systems[0]["m"], N=systems[0]["n"] + systems[0]["m"])
     else:
         base = synth.load_cvxqp1()
@@ -292,7 +290,7 @@ def run_batch(args, rank, local_rank, world):
     bs = BatchSolver(systems, facs, opts, device=local_rank)
     t_setup = time.perf_counter() - t0
     rhs = [w["rhs"] for w in systems]
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         bs.solve("cpminres", rhs, opts)
     if world > 1:
         dist.barrier()
@@ -301,38 +299,99 @@ def run_batch(args, rank, local_rank, world):
     iters = 0
     dev_ms = 0.0
     launches = 0
-    for _ in range(args.steps):
+    solved = 1
+    for _ in range(steps):
         xs, st = bs.solve("cpminres", rhs, opts)
         iters += sum(d["niters"] for d in st)
+        solved = min(solved, min(int(d["solved"]) for d in st))
         dev_ms += bs.last_ms
         launches += bs.last_launches
-        if world > 1:
-            red = torch.tensor([min(int(d["solved"]) for d in st)], device="cuda")
-            dist.all_reduce(red, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t1
-    tt = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([wall, dev_ms, float(-solved)], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([float(iters)], dtype=torch.float64, device="cuda")
     if world > 1:
+        # result gathering / global convergence reduction (the only collectives of the path)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        wall_max, dev_max = tt.tolist()
-        print(json.dumps({
-            "metric": "krylov_iterations_per_second", "value": cnt.item() / wall_max, "unit": "iterations/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
-            "higher_is_better": True, "scaling": "weak" if args.batch_per_gpu > 0 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ipm_batch", "g": args.g, "systems": total, "n": base["n"], "m": base["m"], "solver": "cpminres",
-                       "opts": opts, "systems_per_rank": hi - lo, "device_ms_per_step": dev_max / args.steps,
-                       "setup_s": t_setup, "note": "end to end through the host-pointer batch ABI (H2D rhs, D2H solutions inside the timed region)"},
-            "e2e": {"value": cnt.item() / wall_max, "unit": "iterations/s",
-                    "h2d_bytes_per_step": 8 * base["N"] * (hi - lo), "d2h_bytes_per_step": 8 * base["N"] * (hi - lo)},
-            "gpu_launches": launches}))
     bs.close()
+    if rank != 0:
+        return None
+    wall_max, dev_max, neg_solved = tt.tolist()
+    return {
+        "metric": "krylov_iterations_per_second", "value": cnt.item() / wall_max, "unit": "iterations/s",
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": 1e3 * wall_max / steps,
+        "higher_is_better": True, "scaling": "weak" if per_gpu > 0 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ipm_batch", "g": g, "systems": total, "n": base["n"], "m": base["m"], "solver": "cpminres",
+                   "opts": opts, "systems_per_rank": hi - lo, "device_ms_per_step": dev_max / steps, "all_solved": bool(neg_solved < 0),
+                   "setup_s": t_setup, "note": "end to end through the host-pointer batch ABI (H2D rhs, D2H solutions inside the timed region)"},
+        "e2e": {"value": cnt.item() / wall_max, "unit": "iterations/s",
+                "h2d_bytes_per_step": 8 * base["N"] * (hi - lo), "d2h_bytes_per_step": 8 * base["N"] * (hi - lo)},
+        "gpu_launches": launches}
+
+
+def run_batch(args, rank, local_rank, world):
+    """`--workload ipm_batch`: BASELINE cfg 5 as a line of its own (also reported as the
+    `cfg5_ipm_batch` section of the default line)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = batch_measure(args, rank, local_rank, world, args.steps, args.warmup, total=args.batch, per_gpu=args.batch_per_gpu, g=args.g)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def stress_section(args, torch, peak):
+    """SURVEY 8d stress variant of cfg 3 at full size (k = 6 entries per row of B inside a 64-wide
+    window: nnz(K) ~ 10.1 M, a FILLED factor with hundreds of dependency levels -- the deep
+    sparse triangular solves the k = 2 headline system does not exercise).  Rank 0, untimed set-up
+    reported apart; the solve is timed like the headline (CUDA events of the one launch)."""
+    from cpkrylov_b200 import _lib, synth
+    from cpkrylov_b200.operators import opLDL2, KktSystem
+    from cpkrylov_b200.solvers import _fill_opts, apply_opts_to_M
+    L = _lib.lib()
+    t0 = time.perf_counter()
+    s = synth.kkt_lap3d(g=args.stress_g, k=6, window=64)
+    solver, opts = "cpcg", dict(atol=1e-6, rtol=1e-6)
+    n, m = s["n"], s["m"]
+    N = n + m
+    M = opLDL2(s["G"], s["B"], -s["C"])
+    S = KktSystem(s["H"], s["C"], M)
+    apply_opts_to_M(M, opts)
+    info = M.info()
+    t_setup = time.perf_counter() - t0
+    sid, o = _fill_opts(solver, opts, n, m)
+    cap = int(L.cpk_hist_capacity(sid, ct.byref(o)))
+    hist = np.zeros((3, cap))
+    b_dev = torch.from_numpy(s["rhs"]).to("cuda")
+    x_dev = torch.empty(N, dtype=torch.float64, device="cuda")
+    ms = []
+    for _ in range(2 + args.stress_steps):
+        st = _lib.StatsStruct()
+        _lib.check(L.cpk_reg_solve(S.handle, sid, b_dev.data_ptr(), ct.byref(o), x_dev.data_ptr(), _lib.MEM_DEVICE,
+                                   ct.byref(st), hist.ctypes.data, cap))
+        ms.append(st.t_solve_ms)
+    d = _lib.stats_to_dict(st)
+    kernel_ms = float(np.mean(ms[2:]))
+    bytes_solve, parts = algorithmic_bytes(s, info, solver, d)
+    x_gpu = x_dev.cpu().numpy()
+    out = {"config": dict(s["params"], solver=solver, opts=opts, iters_per_solve=d["niters"], solved=d["solved"],
+                          relerr_vs_xstar=float(np.linalg.norm(x_gpu - s["xstar"]) / np.linalg.norm(s["xstar"])),
+                          setup_s=t_setup, t_factor_s=M.t_factor, t_upload_s=M.t_upload, ldl=info),
+           "steps": args.stress_steps, "ms_per_step": kernel_ms, "value": 1e3 * d["niters"] / kernel_ms, "unit": "iterations/s",
+           "roofline": {"bound": "hbm", "achieved": bytes_solve / kernel_ms / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_solve / kernel_ms / 1e6 / peak, "algorithmic_bytes_per_launch": bytes_solve, "bytes_parts": parts,
+                        "ldl_solves": d["nldlsolve"]}}
+    if not args.no_parity:
+        out["parity"] = parity_section(s, solver, opts, M.factors, x_gpu, d)
+    S.close()
+    return out
 
 
 def main():
@@ -356,6 +415,10 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="ipm_batch: systems PER GPU (weak scaling) instead of --batch in total")
     ap.add_argument("--no-parts", action="store_true", help="skip the stand-alone per-kernel roofline section")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle run")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg 5 (ipm_batch) and stress (k=6 windowed) sections of the default line")
+    ap.add_argument("--stress-g", type=int, default=100)
+    ap.add_argument("--stress-steps", type=int, default=3)
+    ap.add_argument("--extras-batch-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -538,11 +601,22 @@ def main():
             line["cpu_baseline"] = {"value": so["niters"] / so["stime"], "unit": "iterations/s", "cores": blas_threads(), "kind": "port",
                                     "sample": "first %d iterations of the same solve (oracle/cpk_oracle.py + oracle/kernels.c: sparse kernels "
                                               "single-threaded, NumPy BLAS-1 on the BLAS thread pool; host has %d cores)" % (kit, os.cpu_count())}
+    S.close()
+    extras = not args.no_extras and args.workload == "kkt_lap3d" and args.k == 2 and not args.g
+    if extras:
+        # BASELINE cfg 5, sharded over the ranks of THIS run (strong scaling: 256 systems in total)
+        b5 = batch_measure(args, rank, local_rank, world, args.extras_batch_steps, 3, total=args.batch)
+        if rank == 0:
+            line["cfg5_ipm_batch"] = {k: b5[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "e2e", "gpu_launches")}
+        if world > 1:
+            dist.barrier()
+    if rank == 0:
+        if extras:
+            line["stress_k6"] = stress_section(args, torch, peak_gbs()[0])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    S.close()
 
 
 if __name__ == "__main__":

@@ -3,12 +3,12 @@
 # usage: LIBS="b200 r1 ..." scripts/ab_r2.sh
 for lib in ${LIBS:-b200}; do
   export CPK_LIB_PATH=$PWD/cpkrylov_b200/libcpk_$lib.so
-  python bench.py --no-cpu-baseline --no-parts --no-parity --steps 20 --profile 2>&1 | tail -1 | python -c "
+  python bench.py --no-cpu-baseline --no-parts --no-parity --no-extras --steps 20 --profile 2>&1 | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); c=d['config']
 print('$lib', 'cfg3 cpcg ms/solve %.4f iters %d it/s %d frac %.3f e2e %d relerr %.2e' % (c['device_ms_per_step'], c['iters_per_solve'], d['value'], d['roofline']['frac'], d['e2e']['value'], c['relerr_vs_xstar']), 'phases', {k: round(v,3) for k,v in d.get('phase_share',{}).items()}, 'setup_s %.2f' % c['setup_s'])
 " || echo "$lib bench failed"
-  python bench.py --no-cpu-baseline --no-parts --no-parity --steps 20 2>&1 | tail -1 | python -c "
+  python bench.py --no-cpu-baseline --no-parts --no-parity --no-extras --steps 20 2>&1 | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); c=d['config']
 print('$lib', 'cfg3 cpcg (no profile) ms/solve %.4f it/s %d frac %.3f' % (c['device_ms_per_step'], d['value'], d['roofline']['frac']))

@@ -1,15 +1,10 @@
 mkdir -p gpurun_out
-out=gpurun_out/r2_stress23.log; : > $out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "stress or walk_variants or opldl2 or full_size" 2>&1 | tail -3 | tee -a $out
-env A=1 timeout 300 python scripts/stress_env_probe.py 40 "g40" 2>&1 | tail -1 | tee -a $out
-env A=1 timeout 300 python scripts/stress_env_probe.py 60 "g60" 2>&1 | tail -1 | tee -a $out
-for W in 32 64; do
-echo "== CPK_LDL_WIDE_ROW=$W" | tee -a $out
-CPK_VERBOSE=1 CPK_LDL_WIDE_ROW=$W timeout 900 python bench.py --k 6 --window 64 --steps 5 --warmup 3 --no-cpu-baseline --no-parts --profile 2>gpurun_out/r2_stress23_W$W.err | tail -1 | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); c=d['config']
-print('stress g100 ms/solve %.3f iters %d frac %.4f setup_s %.1f parity %s phases %s' % (c['device_ms_per_step'], c['iters_per_solve'], d['roofline']['frac'], c['setup_s'], d['parity']['relerr_vs_oracle'], {k: round(v,3) for k,v in d.get('phase_share',{}).items()}))" | tee -a $out
-done
-export LIBS=b200
-timeout 600 scripts/ab_r2.sh 2>&1 | tee gpurun_out/r2_ab23.log
-timeout 600 python scripts/compact_probe.py --quick 2>&1 | grep -A12 "^default" | grep "us_per_iter\|cvxqp" | tee -a $out
+( time python bench.py > gpurun_out/r2_bench24.json 2> gpurun_out/r2_bench24.err ) 2>&1 | tail -3
+tail -3 gpurun_out/r2_bench24.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench24.json').read().strip().splitlines()[-1])
+print({k:(v if not isinstance(v,dict) else '...') for k,v in d.items()})
+print('cfg5', {k:v for k,v in d['cfg5_ipm_batch'].items() if k!='config'}, d['cfg5_ipm_batch']['config']['device_ms_per_step'])
+s=d['stress_k6']; print('stress', s['ms_per_step'], s['value'], s['roofline']['frac'], s['config']['ldl'], s['config']['setup_s'], s.get('parity'))
+PY
