@@ -515,6 +515,51 @@ __device__ void run_cpsymmlq(Ctx<Team> &c, const double *b, double *X)
 }
 
 // ---------------------------------------------------------------------------
+// v_i = init(i) - sum_j cf[j] * B[cols[j]][i], subtracted in j order (the order of the
+// reference's loops cpgmres.m:214-218, cpdqgmres.m:210-216 / :255-258), then fin(i, v_i).
+// The pass streams nc columns of the basis: two consecutive elements per thread (16-byte
+// loads) and the loads of four columns issued before their subtractions, so that a thread
+// has 64 bytes per vector group in flight instead of one 8-byte load per loop trip.
+// cols / cf live in shared memory.
+// ---------------------------------------------------------------------------
+template <class Team, class Init, class Fin>
+__device__ __forceinline__ void basis_combine(const Team &T, int N, const double *B, const int *cols, const double *cf, int nc,
+                                              Init &&init, Fin &&fin)
+{
+    const int tid = T.tid, nth = T.nthreads;
+    if ((N & 1) == 0 && (reinterpret_cast<size_t>(B) & 15) == 0) {
+        const int NP = N >> 1;
+        for (int p = tid; p < NP; p += nth) {
+            const int i = 2 * p;
+            double v0 = init(i), v1 = init(i + 1);
+            int j = 0;
+            for (; j + 4 <= nc; j += 4) {
+                double2 a[4]; double h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a[q] = *reinterpret_cast<const double2 *>(B + (size_t)cols[j + q] * N + i);
+                    h[q] = cf[j + q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { v0 = v0 - h[q] * a[q].x; v1 = v1 - h[q] * a[q].y; }
+            }
+            for (; j < nc; ++j) {
+                const double2 a = *reinterpret_cast<const double2 *>(B + (size_t)cols[j] * N + i);
+                const double h = cf[j];
+                v0 = v0 - h * a.x; v1 = v1 - h * a.y;
+            }
+            fin(i, v0); fin(i + 1, v1);
+        }
+    } else {
+        for (int i = tid; i < N; i += nth) {
+            double v = init(i);
+            for (int j = 0; j < nc; ++j) v = v - cf[j] * B[(size_t)cols[j] * N + i];
+            fin(i, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Arnoldi helpers for cpgmres / cpdqgmres.  The reference's Gram-Schmidt
 // coefficients use the FIXED u, t (cpgmres.m:215, cpdqgmres.m:213), so all of
 // them come out of one pass over the basis; the subtraction then runs in the
@@ -631,12 +676,9 @@ __device__ void run_cpgmres(Ctx<Team> &c, const double *b, double *X)
             c.apply(U, true, W);                                    // :211
             multi_dot(c, VQ, cols, k, U, hs);                       // :215
             part[0] = 0.0;
-            TEAM_FOR(T, i, N) {                                     // :212-218
-                double v = (i < n) ? W[i] : Vk[i] - W[i];
-                for (int j = 0; j < k; ++j) v = v - hs[j] * VQ[(size_t)j * N + i];
-                Vk1[i] = v;
-                part[0] += U[i] * v;
-            }
+            basis_combine(T, N, VQ, cols, hs, k,                    // :212-218
+                          [&](int i) { return (i < n) ? W[i] : Vk[i] - W[i]; },
+                          [&](int i, double v) { Vk1[i] = v; part[0] += U[i] * v; });
             T.template reduce<1>(part);
             if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)((outer - 1) * R + k), part[0]); return; }
             const double hk1 = sqrt(part[0]);                       // :219
@@ -754,12 +796,9 @@ __device__ void run_cpdqgmres(Ctx<Team> &c, const double *b, double *X)
         T.cta_sync();
         multi_dot(c, VQ, cols, nc, U, hs);                          // :213
         part[0] = 0.0;
-        TEAM_FOR(T, i, N) {                                         // :208-216
-            double v = (i < n) ? W[i] : Vk[i] - W[i];
-            for (int j = 0; j < nc; ++j) v = v - hs[j] * VQ[(size_t)cols[j] * N + i];
-            Vk1[i] = v;
-            part[0] += U[i] * v;
-        }
+        basis_combine(T, N, VQ, cols, hs, nc,                       // :208-216
+                      [&](int i) { return (i < n) ? W[i] : Vk[i] - W[i]; },
+                      [&](int i, double v) { Vk1[i] = v; part[0] += U[i] * v; });
         T.template reduce<1>(part);
         if (part[0] < 0.0) { c.fail(CPK_ERR_BREAKDOWN_, (int)k, part[0]); return; }
         const double hk1 = sqrt(part[0]);                           // :218
@@ -794,14 +833,16 @@ __device__ void run_cpdqgmres(Ctx<Team> &c, const double *b, double *X)
         T.cta_sync();
         const double hk2 = s_scal[1], gk = s_scal[2];
         double *PVk = PVQ + (size_t)kpos * N;
-        TEAM_FOR(T, i, N) {
-            if (hk1 != 0.0) Vk1[i] = Vk1[i] / hk1;                  // :222-225
-            double p = Vk[i];                                       // :253-263
-            for (int j = 0; j < np; ++j) p = p - pcf[j] * PVQ[(size_t)cols[j] * N + i];
-            p = p / hk2;
-            PVk[i] = p;
-            X[i] = (i < n) ? X[i] + gk * p : X[i] - gk * p;         // :264-265
-        }
+        basis_combine(T, N, PVQ, cols, pcf, np,                     // :253-263
+                      [&](int i) {
+                          if (hk1 != 0.0) Vk1[i] = Vk1[i] / hk1;    // :222-225
+                          return Vk[i];
+                      },
+                      [&](int i, double p) {
+                          p = p / hk2;
+                          PVk[i] = p;
+                          X[i] = (i < n) ? X[i] + gk * p : X[i] - gk * p;   // :264-265
+                      });
         residNorm = s_scal[0];                                      // :268
         c.hist(0, k, residNorm);
         T.sync();

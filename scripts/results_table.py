@@ -41,4 +41,4 @@ w4 = synth.kkt_convdiff(g=126)
 for solver, opts in [("cpdqgmres", {"mem": 20}), ("cpdqgmres", {"mem": 50}), ("cpgmres", {"restart": 50})]:
     o = dict(opts, atol=1e-6, rtol=1e-6, itmax=500, nitref=1, force_itref=True)
     r = run(w4, solver, o, reps=3, mem=opts.get("mem", 0), restart=opts.get("restart", 0)); r["config"] = "cfg4 kkt_convdiff g=126"; out.append(r); print(json.dumps(r), flush=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r1_results_table.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", (os.environ.get("CPK_RESULTS_TAG", "r2")) + "_results_table.json"), "w"), indent=1)
