@@ -599,10 +599,23 @@ __device__ void multi_dot(Ctx<Team> &c, const double *VQ, const int *cols, int n
         const double *colp[kRedMax];
 #pragma unroll
         for (int j = 0; j < kRedMax; ++j) { acc[j] = 0.0; colp[j] = VQ + (size_t)cols[j0 + min(j, nv - 1)] * N; }
-        TEAM_FOR(T, i, N) {
-            const double u = U[i];
+        if ((N & 1) == 0 && ((reinterpret_cast<size_t>(VQ) | reinterpret_cast<size_t>(U)) & 15) == 0) {
+            // two consecutive elements per thread: 16-byte loads, 128 bytes per thread in flight
+            const int NP = N >> 1;
+            for (int p = T.tid, stride = T.nthreads; p < NP; p += stride) {
+                const double2 u = *reinterpret_cast<const double2 *>(U + 2 * p);
+                double2 a[kRedMax];
 #pragma unroll
-            for (int j = 0; j < kRedMax; ++j) acc[j] += colp[j][i] * u;
+                for (int j = 0; j < kRedMax; ++j) a[j] = *reinterpret_cast<const double2 *>(colp[j] + 2 * p);
+#pragma unroll
+                for (int j = 0; j < kRedMax; ++j) { acc[j] += a[j].x * u.x; acc[j] += a[j].y * u.y; }
+            }
+        } else {
+            TEAM_FOR(T, i, N) {
+                const double u = U[i];
+#pragma unroll
+                for (int j = 0; j < kRedMax; ++j) acc[j] += colp[j][i] * u;
+            }
         }
         T.template wide_store<kRedMax>(acc, j0, nv, hs);
     }
