@@ -211,6 +211,7 @@ __device__ __forceinline__ int item_slot(const DevSweep &S, int t, int lane)
 // col -1 = padding.
 constexpr int kCwBlock = 16384;     // bytes per stream block
 constexpr int kCwStages = 3;        // ring depth
+constexpr int kCwStage = 512;       // doubles of staging area behind the sweep values (chain merging, cpk_host_compact.hpp)
 #ifndef CPK_CW_WARPS
 #define CPK_CW_WARPS 12
 #endif
@@ -232,7 +233,7 @@ struct DevCompact {
 };
 __host__ __device__ inline size_t cw_smem_bytes(int N, bool one_vector)
 {
-    return (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16 + (size_t)(one_vector ? 8 : 16) * N;
+    return (size_t)kCwStages * kCwBlock + 8 * kCwStages + 16 + (size_t)(one_vector ? 8 : 16) * N + (size_t)8 * kCwStage;
 }
 
 struct DevLdl {

@@ -1206,9 +1206,12 @@ static int cpk_ldl2_create_impl(cpk_handle *out, const cpk_csc *A, const cpk_csc
         // (below ~24 levels the level walk's two barriers-with-L2-round-trips per level cost less
         // than the compact walk's gather / scatter of the whole vector; CPK_LDL_COMPACT=1 forces it)
         if (compact_walk) {
-            cw_sweep(cws, N, Lrows, lf, nlf, 0, 0);         // w_i -= L(i,:) w        target w_i,  deps w
+            // (a device-factorized operator rewrites the factor values inside the stream: no merged chains there)
+            CwStage stg;
+            if (!g_force_compact && !getenv("CPK_CW_NO_CHAINS")) stg.base = m.cw.yoff + N;
+            cw_sweep(cws, N, Lrows, lf, nlf, 0, 0, &stg);         // w_i -= L(i,:) w        target w_i,  deps w
             cw_dpass(cws, N, d, e, partner);                // y = D^-1 w
-            cw_sweep(cws, N, Lcols, lb, nlb, m.cw.yoff, m.cw.yoff);      // y_i -= L(:,i)' y       target y_i,  deps y
+            cw_sweep(cws, N, Lcols, lb, nlb, m.cw.yoff, m.cw.yoff, &stg);      // y_i -= L(:,i)' y       target y_i,  deps y
             cws.flush();
             std::vector<int> p32(N);
             for (int i = 0; i < N; ++i) p32[i] = (int)p[i];
@@ -1283,10 +1286,12 @@ extern "C" int cpk_debug_cw_stream(const cpk_csc *L, const cpk_csc *D, const int
     int rc = parse_ldl(L, D, perm, N, &HL);
     if (rc) return rc;
     CwStream cws;
-    cw_sweep(cws, N, HL.Lrows, HL.lf, HL.nlf, 0, 0);
-    cw_dpass(cws, N, HL.d, HL.e, HL.partner);
     const int yoff = HL.n2 == 0 ? 0 : N;
-    cw_sweep(cws, N, HL.Lcols, HL.lb, HL.nlb, yoff, yoff);
+    CwStage stg;
+    if (!getenv("CPK_CW_NO_CHAINS")) stg.base = yoff + N;
+    cw_sweep(cws, N, HL.Lrows, HL.lf, HL.nlf, 0, 0, &stg);
+    cw_dpass(cws, N, HL.d, HL.e, HL.partner);
+    cw_sweep(cws, N, HL.Lcols, HL.lb, HL.nlb, yoff, yoff, &stg);
     cws.flush();
     *nbytes = (int64_t)cws.bytes.size();
     if (buf && cap >= *nbytes) memcpy(buf, cws.bytes.data(), cws.bytes.size());

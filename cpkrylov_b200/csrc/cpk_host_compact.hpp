@@ -95,83 +95,195 @@ static void cw_put(std::vector<unsigned char> &b, const void *src, size_t n)
     if (n) b.insert(b.end(), s, s + n);
 }
 
-// items of one sweep direction.  R.row(i) = dependency list of LDL row i as (row id, value);
-// `toff`/`coff`: offsets of the target and of the dependencies in the shared vector sv[2N].
-static void cw_sweep(CwStream &S, int N, const HCsr &R, const std::vector<int> &lev, int nlev, int toff, int coff)
+// One row of a level, addresses absolute in the shared vector: sv[tgt] -= sum val_k * sv[col_k]
+struct CwRowH { int tgt; std::vector<int> col; std::vector<double> val; int len() const { return (int)col.size(); } };
+
+// Emits the rows of ONE dependency level (independent of one another): short rows 32 per item,
+// long rows one warp each (in parts of <= 512 entries; the extra parts follow as levels of their own).
+static void cw_emit_level(CwStream &S, std::vector<CwRowH> &rows)
 {
     constexpr int kMaxWidth = 16;           // entries per lane in one item
+    if (rows.empty()) return;
+    typedef std::vector<CwItemH> Items;
+    std::stable_sort(rows.begin(), rows.end(), [&](const CwRowH &a, const CwRowH &b) { return a.len() < b.len(); });
+    Items first;
+    std::vector<Items> later;           // later[j-1] = parts j of the long rows
+    size_t k = 0;
+    // short rows: up to 32 per item, one lane each
+    while (k < rows.size() && rows[k].len() <= kLongRow) {
+        size_t k1 = k;
+        int width = 0;
+        while (k1 < rows.size() && k1 - k < 32 && rows[k1].len() <= kLongRow) { width = std::max(width, rows[k1].len()); ++k1; }
+        const int stride = ((int)(k1 - k) + 3) & ~3;        // lanes stored (idle lanes of a thin item are not)
+        CwItemH it{width <= 2 ? CW_ROWS2 : CW_ROWS, width, stride, 0, {}};
+        if (width <= 2) {
+            // one 32-byte record per lane: {target, col0, col1, 0, val0, val1}
+            for (int q = 0; q < stride; ++q) {
+                int rec_i[4] = {-1, -1, -1, 0};
+                double rec_v[2] = {0.0, 0.0};
+                if (k + q < k1) {
+                    const CwRowH &r = rows[k + q];
+                    rec_i[0] = r.tgt;
+                    for (int j = 0; j < r.len(); ++j) { rec_i[1 + j] = r.col[j]; rec_v[j] = r.val[j]; }
+                }
+                cw_put(it.data, rec_i, 16);
+                cw_put(it.data, rec_v, 16);
+            }
+        } else {
+            int tgt[32];
+            for (int q = 0; q < 32; ++q) tgt[q] = (k + q < k1) ? rows[k + q].tgt : -1;
+            cw_put(it.data, tgt, (size_t)4 * stride);
+            std::vector<double> val((size_t)width * stride, 0.0);
+            std::vector<int> col((size_t)width * stride, -1);
+            for (size_t q = k; q < k1; ++q) {
+                const CwRowH &r = rows[q];
+                for (int j = 0; j < r.len(); ++j) {
+                    val[(size_t)j * stride + (q - k)] = r.val[j];
+                    col[(size_t)j * stride + (q - k)] = r.col[j];
+                }
+            }
+            cw_put(it.data, val.data(), val.size() * 8);
+            cw_put(it.data, col.data(), col.size() * 4);
+        }
+        first.push_back(std::move(it));
+        k = k1;
+    }
+    // long rows: the 32 lanes share the row, <= 32*kMaxWidth entries per part
+    for (; k < rows.size(); ++k) {
+        const CwRowH &r = rows[k];
+        const int len = r.len();
+        int part = 0;
+        for (int e0 = 0; e0 < len; e0 += 32 * kMaxWidth, ++part) {
+            const int cnt = std::min(len - e0, 32 * kMaxWidth);
+            const int width = (cnt + 31) / 32;
+            CwItemH it{CW_WARPROW, width, 32, r.tgt, {}};
+            std::vector<double> val((size_t)width * 32, 0.0);
+            std::vector<int> col((size_t)width * 32, -1);
+            for (int j = 0; j < cnt; ++j) { val[j] = r.val[e0 + j]; col[j] = r.col[e0 + j]; }
+            cw_put(it.data, val.data(), val.size() * 8);
+            cw_put(it.data, col.data(), col.size() * 4);
+            if (part == 0) first.push_back(std::move(it));
+            else {
+                if ((int)later.size() < part) later.resize(part);
+                later[part - 1].push_back(std::move(it));
+            }
+        }
+    }
+    S.level(first);
+    for (auto &st : later) S.level(st);
+}
+
+// Slots of the staging area behind the sweep values (see cw_sweep): DevCompact / cw_smem_bytes reserve them.
+struct CwStage { int base = -1, used = 0; };        // base < 0: chain merging off
+
+// items of one sweep direction.  R.row(i) = dependency list of LDL row i as (row id, value);
+// `toff`/`coff`: offsets of the target and of the dependencies in the shared vector sv[2N].
+//
+// CHAIN MERGING (stage.base >= 0).  A level costs the walkers a barrier and a slot fetch (~400 cycles)
+// on top of its arithmetic, and the tail of a filled factor is a chain of levels of ONE or two rows
+// (cvxqp1: 47 consecutive one-row levels).  A run of such levels is rewritten as two levels: the
+// rows of the run substitute their in-run dependencies, so that each becomes a linear form in the
+// values the vector holds when the run starts -- sv[i] = sv[i] + delta_i, delta_i = -sum_c F_i(c) sv[c],
+// F_i = L_i,: - sum_{j in run} L_ij F_j -- and, the sweep being in place, the deltas are first
+// collected in a staging area behind the vector (level 1: nobody's target is anybody's input) and
+// then added to their rows (level 2).  The staging slots are zeroed when a solve starts, every slot
+// is used by one row only.  Guards: entries <= 8 x the original ones, |F| <= 1e3 x max|L|; a run the guards cut short continues as a new group.
+static void cw_sweep(CwStream &S, int N, const HCsr &R, const std::vector<int> &lev, int nlev, int toff, int coff, CwStage *stage = nullptr)
+{
     std::vector<std::vector<int>> byLevel(nlev);
     for (int i = 0; i < N; ++i) if (R.len(i) > 0) byLevel[lev[i]].push_back(i);
-    typedef std::vector<CwItemH> Items;
-    auto emit = [&](Items &&items) { S.level(items); };
+    // ---- runs of tiny levels
+    static const int kChainItems = [] { const char *e = getenv("CPK_CW_CHAIN_ITEMS"); return e ? atoi(e) : 2; }();
+    static const int kChainFill = [] { const char *e = getenv("CPK_CW_CHAIN_FILL"); return e ? atoi(e) : 8; }();
+    constexpr int kChainMin = 4;
+    std::vector<int> run_end(nlev, -1);         // run_end[l0] = last level of the run that starts at l0
+    if (stage && stage->base >= 0) {
+        auto tiny = [&](int l) {
+            if (byLevel[l].empty()) return false;
+            int nshort = 0, nlong = 0;
+            for (int r : byLevel[l]) { if (R.len(r) <= kLongRow) ++nshort; else ++nlong; }
+            return (nshort + 31) / 32 + nlong <= kChainItems;
+        };
+        for (int l = 0; l < nlev;) {
+            if (!tiny(l)) { ++l; continue; }
+            int e = l;
+            while (e + 1 < nlev && tiny(e + 1)) ++e;
+            if (e - l + 1 >= kChainMin) run_end[l] = e;
+            l = e + 1;
+        }
+    }
+    double maxL = 1.0;
+    for (double v : R.val) maxL = std::max(maxL, std::fabs(v));
+    std::vector<double> acc;
+    std::vector<int> mark, touched;
     for (int l = 0; l < nlev; ++l) {
+        if (run_end[l] >= 0) {
+            // ---- try to merge the levels l .. run_end[l] (or a prefix of the run)
+            if (acc.empty()) { acc.assign((size_t)N, 0.0); mark.assign((size_t)N, -1); }
+            std::vector<int> rows_g;                          // rows of the merged levels, level order
+            std::unordered_map<int, size_t> pos;              // row -> index in F
+            std::vector<std::vector<std::pair<int, double>>> F;
+            long long orig = 0, fill = 0;
+            int last = l - 1;
+            for (int ll = l; ll <= run_end[l]; ++ll) {
+                bool ok = stage->used + (int)rows_g.size() + (int)byLevel[ll].size() <= kCwStage;
+                std::vector<std::vector<std::pair<int, double>>> Fl;
+                long long lorig = 0, lfill = 0;
+                for (size_t q = 0; q < byLevel[ll].size() && ok; ++q) {
+                    const int i = byLevel[ll][q];
+                    touched.clear();
+                    auto add = [&](int c, double v) {
+                        if (mark[c] != i) { mark[c] = i; acc[c] = 0.0; touched.push_back(c); }
+                        acc[c] += v;
+                    };
+                    for (int64_t k = R.ptr[i]; k < R.ptr[i + 1]; ++k) {
+                        const int j = R.col[k]; const double a = R.val[k];
+                        ++lorig;
+                        add(j, a);
+                        auto it = pos.find(j);
+                        if (it != pos.end()) for (auto &x : F[it->second]) add(x.first, -a * x.second);
+                    }
+                    std::sort(touched.begin(), touched.end());
+                    std::vector<std::pair<int, double>> fi;
+                    for (int c : touched) { fi.emplace_back(c, acc[c]); if (!(std::fabs(acc[c]) <= 1e3 * maxL)) ok = false; }
+                    lfill += (long long)fi.size();
+                    Fl.push_back(std::move(fi));
+                }
+                if (ok && fill + lfill > (long long)kChainFill * (orig + lorig) + 256) ok = false;
+                if (!ok) break;
+                for (size_t q = 0; q < byLevel[ll].size(); ++q) { pos[byLevel[ll][q]] = F.size(); rows_g.push_back(byLevel[ll][q]); F.push_back(std::move(Fl[q])); }
+                orig += lorig; fill += lfill; last = ll;
+            }
+            if (getenv("CPK_VERBOSE"))
+                fprintf(stderr, "[cpk] compact walk: run of tiny levels %d..%d, merged %d..%d (%zu rows, %lld -> %lld entries, staging used %d)\n",
+                        l, run_end[l], l, last, rows_g.size(), orig, fill, stage->used);
+            if (last - l + 1 >= kChainMin) {
+                std::vector<CwRowH> comp, commit;
+                for (size_t q = 0; q < rows_g.size(); ++q) {
+                    const int slot = stage->base + stage->used++;
+                    CwRowH r{slot, {}, {}};
+                    for (auto &x : F[q]) { r.col.push_back(coff + x.first); r.val.push_back(x.second); }
+                    comp.push_back(std::move(r));
+                    commit.push_back(CwRowH{toff + rows_g[q], {slot}, {-1.0}});
+                }
+                cw_emit_level(S, comp);
+                cw_emit_level(S, commit);
+                if (last < run_end[l]) run_end[last + 1] = run_end[l];      // the rest of the run may form a group of its own
+                l = last;               // the loop's ++l moves past the merged levels
+                continue;
+            }
+            if (l < run_end[l]) run_end[l + 1] = run_end[l];
+        }
         std::vector<int> &rows = byLevel[l];
         if (rows.empty()) continue;
-        std::stable_sort(rows.begin(), rows.end(), [&](int a, int b) { return R.len(a) < R.len(b); });
-        Items first;
-        std::vector<Items> later;           // later[j-1] = parts j of the long rows
-        size_t k = 0;
-        // short rows: up to 32 per item, one lane each
-        while (k < rows.size() && R.len(rows[k]) <= kLongRow) {
-            size_t k1 = k;
-            int width = 0;
-            while (k1 < rows.size() && k1 - k < 32 && R.len(rows[k1]) <= kLongRow) { width = std::max(width, R.len(rows[k1])); ++k1; }
-            const int stride = ((int)(k1 - k) + 3) & ~3;        // lanes stored (idle lanes of a thin item are not)
-            CwItemH it{width <= 2 ? CW_ROWS2 : CW_ROWS, width, stride, 0, {}};
-            if (width <= 2) {
-                // one 32-byte record per lane: {target, col0, col1, 0, val0, val1}
-                for (int q = 0; q < stride; ++q) {
-                    int rec_i[4] = {-1, -1, -1, 0};
-                    double rec_v[2] = {0.0, 0.0};
-                    if (k + q < k1) {
-                        const int r = rows[k + q];
-                        rec_i[0] = toff + r;
-                        for (int j = 0; j < R.len(r); ++j) { rec_i[1 + j] = coff + R.col[R.ptr[r] + j]; rec_v[j] = R.val[R.ptr[r] + j]; }
-                    }
-                    cw_put(it.data, rec_i, 16);
-                    cw_put(it.data, rec_v, 16);
-                }
-            } else {
-                int tgt[32];
-                for (int q = 0; q < 32; ++q) tgt[q] = (k + q < k1) ? toff + rows[k + q] : -1;
-                cw_put(it.data, tgt, (size_t)4 * stride);
-                std::vector<double> val((size_t)width * stride, 0.0);
-                std::vector<int> col((size_t)width * stride, -1);
-                for (size_t q = k; q < k1; ++q) {
-                    const int r = rows[q];
-                    for (int j = 0; j < R.len(r); ++j) {
-                        val[(size_t)j * stride + (q - k)] = R.val[R.ptr[r] + j];
-                        col[(size_t)j * stride + (q - k)] = coff + R.col[R.ptr[r] + j];
-                    }
-                }
-                cw_put(it.data, val.data(), val.size() * 8);
-                cw_put(it.data, col.data(), col.size() * 4);
-            }
-            first.push_back(std::move(it));
-            k = k1;
+        std::vector<CwRowH> lr;
+        lr.reserve(rows.size());
+        for (int r : rows) {
+            CwRowH h{toff + r, {}, {}};
+            for (int64_t k = R.ptr[r]; k < R.ptr[r + 1]; ++k) { h.col.push_back(coff + R.col[k]); h.val.push_back(R.val[k]); }
+            lr.push_back(std::move(h));
         }
-        // long rows: the 32 lanes share the row, <= 32*kMaxWidth entries per part
-        for (; k < rows.size(); ++k) {
-            const int r = rows[k], len = R.len(r);
-            int part = 0;
-            for (int e0 = 0; e0 < len; e0 += 32 * kMaxWidth, ++part) {
-                const int cnt = std::min(len - e0, 32 * kMaxWidth);
-                const int width = (cnt + 31) / 32;
-                CwItemH it{CW_WARPROW, width, 32, toff + r, {}};
-                std::vector<double> val((size_t)width * 32, 0.0);
-                std::vector<int> col((size_t)width * 32, -1);
-                for (int j = 0; j < cnt; ++j) { val[j] = R.val[R.ptr[r] + e0 + j]; col[j] = coff + R.col[R.ptr[r] + e0 + j]; }
-                cw_put(it.data, val.data(), val.size() * 8);
-                cw_put(it.data, col.data(), col.size() * 4);
-                if (part == 0) first.push_back(std::move(it));
-                else {
-                    if ((int)later.size() < part) later.resize(part);
-                    later[part - 1].push_back(std::move(it));
-                }
-            }
-        }
-        emit(std::move(first));
-        for (auto &st : later) emit(std::move(st));
+        cw_emit_level(S, lr);
     }
 }
 

@@ -779,6 +779,8 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
 #pragma unroll
         for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; if (i < N) W.sv[i] = zv[u]; }
     }
+    // staging slots of the merged chains: zero when a solve starts (C.yoff + N = end of the sweep values)
+    for (int i = T.tid; i < kCwStage; i += T.nthreads) W.sv[C.yoff + N + i] = 0.0;
     __syncthreads();
     lap(0);
     // The walk itself is done by the first kCwWarps warps (a level is one warp's dependent

@@ -66,10 +66,12 @@ def run(env_extra):
 
 if __name__ == "__main__":
     allres = {}
-    configs = (("default", {"CPK_VERBOSE": "1"}), ("cta level-walk", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "0"}),
-               ("cta compact", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1"}), ("grid", {"CPK_TEAM": "grid"}),
-               ("grid level barriers", {"CPK_TEAM": "grid", "CPK_LDL_SYNCFREE": "0"}),
-               ("cta level-walk, no merging", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "0", "CPK_LDL_NO_TAIL": "1"}))
+    configs = (("cta compact, no chain merging", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_NO_CHAINS": "1"}),
+               ("cta compact, chains of <= 2 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1"}),
+               ("cta compact, chains of <= 4 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "4"}),
+               ("cta compact, chains of <= 8 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "8"}),
+               ("cta compact, chains of <= 8 items, fill 16", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "8", "CPK_CW_CHAIN_FILL": "16"}),
+               ("default", {}))
     if "--quick" in sys.argv:
         configs = (("default", {"CPK_VERBOSE": "1"}),)
     for label, env in configs:

@@ -21,6 +21,7 @@ BLK = 16384
 NW = 12                              # warps that walk the stream (kCwWarps) = slots per step
 CW_ROWS2, CW_ROWS, CW_WARPROW, CW_DCHUNK = 1, 2, 3, 4
 CW_BARRIER = 16
+STAGE = 512                          # kCwStage
 
 
 def _stream(L, d, e, perm):
@@ -120,7 +121,7 @@ def _walk(buf, N, perm, z, yoff=None):
     N: separate w and y -- 2x2 pivots); default = what the builder chooses for a diagonal D."""
     assert buf.size % BLK == 0 and buf.size > 0
     yoff = 0 if yoff is None else yoff
-    sv = np.zeros(N + yoff)
+    sv = np.zeros(N + yoff + STAGE)          # sweep values + the staging slots of merged chains (zero when a solve starts)
     sv[:N] = z[perm]
     stats = dict(blocks=buf.size // BLK, steps=0, items=0, barriers=0)
     written = set()
@@ -203,10 +204,39 @@ def test_stream_long_rows_are_split(cpk_lib):
     e = np.zeros(N)
     perm = rng.permutation(N).astype(np.int64)
     z = rng.standard_normal(N)
-    y, st = _walk(_stream(L, d, e, perm), N, perm, z)
     ref = _direct(L, d, e, perm, z)
+    import os
+    os.environ["CPK_CW_NO_CHAINS"] = "1"
+    try:
+        y, st = _walk(_stream(L, d, e, perm), N, perm, z)
+    finally:
+        os.environ.pop("CPK_CW_NO_CHAINS")
     assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
     assert st["barriers"] > 2 * N    # one row per level; rows longer than 512 entries take several
+    # with chain merging: runs of one-row levels collapse (as far as the staging area and the guards allow)
+    y2, st2 = _walk(_stream(L, d, e, perm), N, perm, z)
+    assert np.linalg.norm(y2 - ref) <= 1e-9 * np.linalg.norm(ref)
+    assert st2["barriers"] < st["barriers"]
+
+
+def test_chains_of_tiny_levels_are_merged(cpk_lib):
+    """cvxqp1 (SuperLU factor): 47 consecutive one-row levels at the end of the forward sweep --
+    merged into two levels through the staging area; same result, far fewer barriers."""
+    import os
+    L, d, e, perm = load_factors("cvxqp1_m", "superlu")
+    N = d.size
+    z = np.random.default_rng(11).standard_normal(N)
+    ref = _direct(L, d, e, perm, z)
+    os.environ["CPK_CW_NO_CHAINS"] = "1"
+    try:
+        y0, st0 = _walk(_stream(L, d, e, perm), N, perm, z)
+    finally:
+        os.environ.pop("CPK_CW_NO_CHAINS")
+    y1, st1 = _walk(_stream(L, d, e, perm), N, perm, z)
+    assert np.linalg.norm(y0 - ref) <= 1e-9 * np.linalg.norm(ref)
+    assert np.linalg.norm(y1 - ref) <= 1e-9 * np.linalg.norm(ref)
+    assert st1["barriers"] <= st0["barriers"] - 40, (st0, st1)
+    print("compact walk of cvxqp1: without / with chain merging", st0, st1)
 
 
 def test_stream_diagonal_factor(cpk_lib):
