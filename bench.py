@@ -183,18 +183,28 @@ def roofline_parts(torch, L, S, M, s, info, peak, reps=12):
     saved = (M.nitref, M.force_itref)
 
     def timed(call):
-        ts = []
-        for _ in range(reps):
-            flush_l2(torch, junk)
-            st = _lib.StatsStruct()
-            _lib.check(call(ct.byref(st)))
-            ts.append(st.t_solve_ms * 1e3)
-        return float(np.median(ts[2:]))
+        # `us`: L2 flushed by WRITING a buffer larger than the L2 (the launch then also pays for the
+        # write-back of the flush's dirty lines); `us_readflush`: the L2 filled with clean lines of a
+        # buffer that was only read.  Both are CUDA events around the cooperative launch.
+        res = []
+        for writes in (True, False):
+            ts = []
+            for _ in range(reps):
+                if writes:
+                    flush_l2(torch, junk)
+                else:
+                    junk.sum(); torch.cuda.synchronize()
+                st = _lib.StatsStruct()
+                _lib.check(call(ct.byref(st)))
+                ts.append(st.t_solve_ms * 1e3)
+            res.append(float(np.median(ts[2:])))
+        return res
 
     out = {}
-    def put(name, us, nbytes, what):
+    def put(name, us2, nbytes, what):
+        us, us_rf = us2
         gbs = nbytes / us / 1e3
-        out[name] = {"us": us, "bytes": nbytes, "GBs": gbs, "frac": gbs / peak, "what": what}
+        out[name] = {"us": us, "bytes": nbytes, "GBs": gbs, "frac": gbs / peak, "us_readflush": us_rf, "frac_readflush": nbytes / us_rf / 1e3 / peak, "what": what}
     put("spmv_H", timed(lambda st: L.cpk_system_matvec(S.handle, 0, x.data_ptr(), y.data_ptr(), 1, st)), B_H,
         "H*v (cpk_system_matvec), 12 nnz + 4(r+1) + 8c + 8r")
     put("spmv_KP", timed(lambda st: L.cpk_ldl2_matvec(M.handle, x.data_ptr(), y.data_ptr(), 1, st)), B_KP,

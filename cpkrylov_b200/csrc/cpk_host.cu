@@ -825,6 +825,20 @@ static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, in
 // (trivial / fused rows), tail inversion, then the item list (level / sync-free walks) and/or
 // the row-class form (shallow sweeps with a diagonal D).  No device needed.
 // ---------------------------------------------------------------------------
+// substituted rows of the level merging, by LDL row (a dense table: hash maps of a million
+// small vectors were most of the set-up time of a large system)
+struct ExpMap {
+    std::vector<EncRow> rows;
+    std::vector<char> has;
+    size_t count = 0;
+    explicit ExpMap(int N) : rows((size_t)N), has((size_t)N, 0) {}
+    const EncRow *find(int i) const { return has[i] ? &rows[i] : nullptr; }
+    const EncRow &at(int i) const { return rows[i]; }
+    void put(int i, EncRow &&r) { if (!has[i]) { has[i] = 1; ++count; } rows[i] = std::move(r); }
+    void erase(int i) { if (has[i]) { has[i] = 0; --count; EncRow().swap(rows[i]); } }
+    size_t size() const { return count; }
+};
+
 struct SweepBuild {
     HSweep W;
     HRc RC;
@@ -885,7 +899,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
     // one level.  expand(t, grp, gid, acc, orig): encoded dependency list of row t with the
     // dependencies inside group gid substituted (reads expd of rows handled before), `orig` +=
     // its original entry count.  scale(t): what the coefficients of row t are judged against.
-    auto merge_levels = [&](std::vector<int> &lev, const std::vector<char> &skip, bool descending, std::unordered_map<int, EncRow> &expd,
+    auto merge_levels = [&](std::vector<int> &lev, const std::vector<char> &skip, bool descending, ExpMap &expd,
                             auto &&expand, auto &&blocker, auto &&scale_of, auto &&orig_len) {
         int maxlev = -1;
         for (int i = 0; i < N; ++i) if (!skip[i]) maxlev = std::max(maxlev, lev[i]);
@@ -903,7 +917,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
             if (g_levels == 1) for (int t : g_rows) expd.erase(t);      // a lone level keeps its original rows
             g_rows.clear();
         };
-        std::unordered_map<int, EncRow> cand;
+        std::vector<std::pair<int, EncRow>> cand;
         for (int l = 0; l <= maxlev; ++l) {
             const std::vector<int> &rows = by_lev[l];
             bool blk = false;
@@ -923,11 +937,11 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
                     sc = std::max(sc, scale_of(t));
                     if (acc.size() > std::max(tail_len_max, (size_t)3 * (size_t)orig_len(t)) ||
                         (double)(g_fill + lfill) > tail_fill_max * (double)std::max<long long>(g_orig + lorig, 1) + 1024.0) { ok = false; break; }
-                    cand[t] = std::move(acc);
+                    cand.emplace_back(t, std::move(acc));
                 }
                 if (ok && !(growth <= 1e3 * sc)) ok = false;
                 if (ok) {
-                    for (auto &kv : cand) { expd[kv.first] = std::move(kv.second); grp[kv.first] = gid; g_rows.push_back(kv.first); }
+                    for (auto &kv : cand) { expd.put(kv.first, std::move(kv.second)); grp[kv.first] = gid; g_rows.push_back(kv.first); }
                     g_orig += lorig; g_fill += lfill; g_nrows += (long long)rows.size(); g_scale = sc; ++g_levels;
                     joined = true;
                 }
@@ -943,7 +957,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
                         expand(t, grp, -2, acc, g_orig);        // no in-group dependency yet: the encoded original row
                         g_fill += (long long)acc.size();
                         g_scale = std::max(g_scale, scale_of(t));
-                        expd[t] = std::move(acc);
+                        expd.put(t, std::move(acc));
                         g_rows.push_back(t);
                     }
                 }
@@ -953,8 +967,11 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         for (int i = 0; i < N; ++i) if (!skip[i]) lev[i] = grp[i];
     };
     std::vector<int> levf(N, 0), levb(N, 0);
-    std::unordered_map<int, EncRow> tailf, tailb;
+    ExpMap tailf(N), tailb(N);
     std::vector<SweepRow> rowsF, rowsB;
+    const auto tb0 = std::chrono::steady_clock::now();
+    auto tb_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(); };
+    double tb_f = 0.0, tb_b = 0.0;
     {
         // ---------------- forward ----------------
         for (int i = 0; i < N; ++i) {
@@ -971,7 +988,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
                     if (triv[jx]) add_to(acc, (int)(-(p[jx]) - 2), a);
                     else if (grp[jx] == gid) {
                         add_to(acc, (int)(-(p[jx]) - 2), a);            // the z_j part of w_j
-                        for (auto &x : tailf[jx]) add_to(acc, x.first, -a * x.second);
+                        for (auto &x : tailf.at(jx)) add_to(acc, x.first, -a * x.second);
                     } else add_to(acc, jx, a);
                 }
             },
@@ -980,12 +997,13 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
             [&](int t) { return Lrows.len(t); });
         for (int i = 0; i < N; ++i) {
             if (triv[i]) continue;
-            auto it = tailf.find(i);
-            rowsF.push_back({i, levf[i], it == tailf.end() ? Lrows.len(i) : (int)it->second.size()});
+            const EncRow *it = tailf.find(i);
+            rowsF.push_back({i, levf[i], it ? (int)it->size() : Lrows.len(i)});
         }
         W.lev_f_eff = 0;
         for (int i = 0; i < N; ++i) if (!triv[i]) W.lev_f_eff = std::max(W.lev_f_eff, levf[i] + 1);
     }
+    tb_f = tb_ms();
     {
         // ---------------- backward: everything not finished in the forward sweep ----------------
         for (int i = N - 1; i >= 0; --i) {
@@ -1002,7 +1020,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
                     if (!fused[r] && grp[r] == gid) {
                         // y_r = w_r/d_r - sum(in-group deps of r):  a*y_r
                         add_to(acc, triv[r] ? (int)(-(p[r]) - 2) : N + r, a / d[r]);
-                        for (auto &x : tailb[r]) add_to(acc, x.first, -a * x.second);
+                        for (auto &x : tailb.at(r)) add_to(acc, x.first, -a * x.second);
                     } else add_to(acc, r, a);
                 }
             },
@@ -1012,32 +1030,32 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
             [&](int t) { return Lcols.len(t); });
         for (int i = 0; i < N; ++i) {
             if (fused[i]) continue;
-            auto it = tailb.find(i);
-            rowsB.push_back({i, levb[i], it == tailb.end() ? Lcols.len(i) : (int)it->second.size()});
+            const EncRow *it = tailb.find(i);
+            rowsB.push_back({i, levb[i], it ? (int)it->size() : Lcols.len(i)});
         }
         W.lev_b_eff = 0;
         for (int i = 0; i < N; ++i) if (!fused[i]) W.lev_b_eff = std::max(W.lev_b_eff, levb[i] + 1);
         W.tail_f = (long long)tailf.size(); W.tail_b = (long long)tailb.size();
     }
+    tb_b = tb_ms();
     for (int i = 0; i < N; ++i) { W.n_trivial += triv[i]; W.n_fused += fused[i]; }
     // encoded dependency lists of a row in the two sweeps (item-list codes: c >= 0 LDL row id,
     // c >= N forward result of row c - N, c <= -2 input element -c-2)
-    auto entriesF = [&](int r) {
-        auto it = tailf.find(r);
-        if (it != tailf.end()) return it->second;
-        EncRow er;
+    EncRow scratchF, scratchB;
+    auto entriesF = [&](int r) -> const EncRow & {
+        if (const EncRow *it = tailf.find(r)) return *it;
+        scratchF.clear();
         for (int64_t k = Lrows.ptr[r]; k < Lrows.ptr[r + 1]; ++k) {
             const int jx = Lrows.col[k];
-            er.emplace_back(triv[jx] ? (int)(-(p[jx]) - 2) : jx, Lrows.val[k]);
+            scratchF.emplace_back(triv[jx] ? (int)(-(p[jx]) - 2) : jx, Lrows.val[k]);
         }
-        return er;
+        return scratchF;
     };
-    auto entriesB = [&](int r) {
-        auto it = tailb.find(r);
-        if (it != tailb.end()) return it->second;
-        EncRow er;
-        for (int64_t k = Lcols.ptr[r]; k < Lcols.ptr[r + 1]; ++k) er.emplace_back(Lcols.col[k], Lcols.val[k]);
-        return er;
+    auto entriesB = [&](int r) -> const EncRow & {
+        if (const EncRow *it = tailb.find(r)) return *it;
+        scratchB.clear();
+        for (int64_t k = Lcols.ptr[r]; k < Lcols.ptr[r + 1]; ++k) scratchB.emplace_back(Lcols.col[k], Lcols.val[k]);
+        return scratchB;
     };
     // Which form(s) of the sweeps to build.  Shallow sweeps without 2x2 pivots are walked in
     // row-class form (one pass per level) when CPK_LDL_RC=1 asks for it; the item list is then only
@@ -1096,6 +1114,8 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         sweep_append(W, rowsB, p, d, e, partner, grid_warps, entriesB,
                      [&](int r) { return (triv[r] ? F_WDIRECT : 0) | (hasR[r] ? F_STORE : 0) | (partner[r] >= 0 ? F_PARTNER : 0); });
     }
+    if (getenv("CPK_VERBOSE"))
+        fprintf(stderr, "[cpk] build_sweeps ms: merge forward %.1f, merge backward %.1f, item lists %.1f\n", tb_f, tb_b - tb_f, tb_ms() - tb_b);
     if ((int64_t)W.col.size() >= INT32_MAX) return fail(CPK_ERR_UNSUPPORTED, "padded L exceeds int32 indexing");
     SB->have_rc = have_rc; SB->want_items = want_items || !have_rc; SB->walk_deep = walk_deep;
     return CPK_OK;

@@ -51,6 +51,11 @@ static void deal_level(HSweep &W, int first, int n, int nw)
     const int s0 = W.sptr[first];
     std::vector<int> col, sptr(1, s0), rid, pidx, flags, partner;
     std::vector<double> val, d, e, dp;
+    {
+        const size_t ne = (size_t)(W.sptr[first + n] - s0), ns = (size_t)n * 32;
+        col.reserve(ne); val.reserve(ne); sptr.reserve((size_t)n + 1);
+        rid.reserve(ns); pidx.reserve(ns); flags.reserve(ns); partner.reserve(ns); d.reserve(ns); e.reserve(ns); dp.reserve(ns);
+    }
     for (int k = 0; k < n; ++k) {
         const int it = first + order[k];
         const int b = W.sptr[it], en = W.sptr[it + 1];
@@ -122,7 +127,7 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
             if (rows[i0].len > thr) {
                 // one long row = one item, entries spread over the 32 lanes
                 const int r = rows[i0].row;
-                const EncRow er = entries(r);
+                const EncRow &er = entries(r);
                 const size_t width = (er.size() + 31) / 32;
                 const size_t base = W.col.size();
                 W.col.resize(base + width * 32, -1);
@@ -163,7 +168,7 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
                         W.e.push_back(ee[std::min(r, partner[r])]);
                         W.dp.push_back(dd[partner[r]]);
                     } else { W.partner.push_back(-1); W.e.push_back(0.0); W.dp.push_back(1.0); }
-                    const EncRow er = entries(r);
+                    const EncRow &er = entries(r);
                     for (size_t jx = 0; jx < er.size(); ++jx) {
                         W.col[base + jx * 32 + lane] = er[jx].first;
                         W.val[base + jx * 32 + lane] = er[jx].second;

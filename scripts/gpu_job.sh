@@ -1,16 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 python scripts/compact_probe.py > gpurun_out/r2_compact30.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_pytest31.log
+python bench.py > gpurun_out/r2_bench31.json 2> gpurun_out/r2_bench31.err; tail -2 gpurun_out/r2_bench31.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/compact_probe.json'))
-for k,v in d.items():
-    if v is None: print(k, None); continue
-    print(k, {kk:(round(vv['us_per_iter'],1), vv['iters'], '%.1e'%vv['err_vs_oracle']) for kk,vv in v.items() if isinstance(vv,dict)}, 'apply_us', round(v['apply_us'],1), 'walk', v['walk_cycles(gather,ring wait,steps,scatter)'])
+d=json.loads(open('gpurun_out/r2_bench31.json').read().strip().splitlines()[-1])
+c=d['config']
+print('cfg3 ms/solve %.4f it/s %d e2e %d frac %.3f setup_s %.2f (factor %.2f upload %.2f)'%(c['device_ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], c['setup_s'], c['t_factor_s'], c['t_upload_s']))
+for k,v in d['roofline_parts'].items(): print(' ',k,'us %.1f frac %.3f | readflush us %.1f frac %.3f'%(v['us'],v['frac'],v['us_readflush'],v['frac_readflush']))
+b=d['cfg5_ipm_batch']; print('cfg5', b['value'], b['ms_per_step'], b['config']['device_ms_per_step'])
+s=d['stress_k6']; print('stress', s['ms_per_step'], s['roofline']['frac'], s['config']['setup_s'])
 PY
-for env in "CPK_CW_NO_CHAINS=1" "A=1" "CPK_CW_CHAIN_ITEMS=8"; do
-env $env python bench.py --workload ipm_batch --steps 5 --warmup 3 2>&1 | tail -1 | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); c=d['config']
-print('$env batch 256: device ms/step %.3f e2e ms/step %.3f it/s %d' % (c['device_ms_per_step'], d['ms_per_step'], d['value']))"
-done
-timeout 900 python -m pytest tests -m gpu -q -x -k "cvxqp or fixture or batch or cfg5 or device_factor or sequence or matio" 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3

@@ -76,7 +76,9 @@ def test_exprog2_nonsymmetric(cp, meth, extra, kind, team):
 @pytest.mark.parametrize("team", ["cta", "grid"])
 @pytest.mark.parametrize("env", [{"CPK_LDL_SYNCFREE": "1"}, {"CPK_LDL_NO_SHORTCUTS": "1"}, {"CPK_LDL_NO_TAIL": "1"},
                                  {"CPK_LDL_SYNCFREE": "1", "CPK_LDL_NO_TAIL": "1"}, {}, {"CPK_LDL_COMPACT": "1"},
-                                 {"CPK_LDL_RC": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_TAIL": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_SHORTCUTS": "1"}])
+                                 {"CPK_LDL_RC": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_TAIL": "1"}, {"CPK_LDL_RC": "1", "CPK_LDL_NO_SHORTCUTS": "1"},
+                                 {"CPK_LDL_COMPACT": "1", "CPK_CW_NO_CHAINS": "1"}, {"CPK_LDL_TAIL_FILL": "2", "CPK_LDL_TAIL_MAXLEN": "32"},
+                                 {"CPK_LDL_DENSE_META": "1", "CPK_LDL_WIDE_ROW": "8"}])
 def test_ldl_walk_variants_agree(cp, env, team):
     """The LDL' solve has four walks (level-synchronous and sync-free/tagged walks of the item
     list, row-class passes for shallow sweeps with a diagonal D -- CPK_LDL_RC=1 --, and the
