@@ -1,13 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_pytest31.log
-python bench.py > gpurun_out/r2_bench31.json 2> gpurun_out/r2_bench31.err; tail -2 gpurun_out/r2_bench31.err
-python - <<'PY'
+N=${NGPU:-4}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
+tail -2 gpurun_out/r2_bench_n$N.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/r2_bench31.json').read().strip().splitlines()[-1])
-c=d['config']
-print('cfg3 ms/solve %.4f it/s %d e2e %d frac %.3f setup_s %.2f (factor %.2f upload %.2f)'%(c['device_ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], c['setup_s'], c['t_factor_s'], c['t_upload_s']))
-for k,v in d['roofline_parts'].items(): print(' ',k,'us %.1f frac %.3f | readflush us %.1f frac %.3f'%(v['us'],v['frac'],v['us_readflush'],v['frac_readflush']))
-b=d['cfg5_ipm_batch']; print('cfg5', b['value'], b['ms_per_step'], b['config']['device_ms_per_step'])
-s=d['stress_k6']; print('stress', s['ms_per_step'], s['roofline']['frac'], s['config']['setup_s'])
+d=json.loads(open('gpurun_out/r2_bench_n$N.json').read().strip().splitlines()[-1])
+print('n_gpus', d['n_gpus'], 'value', d['value'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'])
+b=d['cfg5_ipm_batch']; print('cfg5', b['n_gpus'], b['value'], b['ms_per_step'], b['config']['systems_per_rank'], b['config']['device_ms_per_step'], b['scaling'])
 PY
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
