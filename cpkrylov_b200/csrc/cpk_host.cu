@@ -869,7 +869,7 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
     // small unit-triangular block, built row by row), so the whole group becomes ONE level that
     // depends only on earlier groups and on the input vector.  Groups grow greedily, level by level,
     // while the substitution stays cheap and tame: entries of the group <= tail_fill_max x the
-    // original ones, coefficients <= 10^3 x the scale of L (L'/D), rows <= max(tail_len_max, 3 x their
+    // original ones (or, for small groups, original + 40 000 per absorbed level, see tail_slack), coefficients <= 10^3 x the scale of L (L'/D), rows <= max(tail_len_max, 3 x their
     // original length).  A fill-free forest-shaped factor (cfg 3 / cfg 4: 19+19 levels) collapses
     // to 1+1 levels; the stress factor to a few dozen.  A level with a 2x2 pivot closes the group.
     // A system that will walk the compact stream keeps the global sweep only as a fallback
@@ -877,7 +877,12 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
     // which is most of the host-side set-up time of a small system.
     static const long long tail_rows_max = [] { const char *e = getenv("CPK_LDL_TAIL_ROWS"); return e ? atoll(e) : 4194304LL; }();
     static const double tail_fill_max = [] { const char *e = getenv("CPK_LDL_TAIL_FILL"); return e ? atof(e) : 6.0; }();
-    static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 256LL); }();
+    static const size_t tail_len_max = [] { const char *e = getenv("CPK_LDL_TAIL_MAXLEN"); return (size_t)(e ? atoll(e) : 512LL); }();
+    // what a level costs in entries: a hop of ~5 us is worth tens of thousands of entries of streamed work on the grid (40 000: measured best across sizes), so a group
+    // may also grow by that much per level it absorbs (up to tail_fill_cap x the original entries) -- small systems
+    // (cvxqp1: 7 876 entries in 70 levels) merge far beyond the relative bound, the wide levels of a large one do not
+    static const double tail_slack = [] { const char *e = getenv("CPK_LDL_TAIL_SLACK"); return e ? atof(e) : 40000.0; }();
+    static const double tail_fill_cap = [] { const char *e = getenv("CPK_LDL_TAIL_CAP"); return e ? atof(e) : 64.0; }();
     static const int merge_lmin = (getenv("CPK_LDL_CUT0") && atoi(getenv("CPK_LDL_CUT0")) == 0) ? 1 : 0;
     const bool merging = !getenv("CPK_LDL_NO_TAIL") && !compact_walk;
     auto add_to = [](std::vector<std::pair<int, double>> &acc, int code, double v) { acc.emplace_back(code, v); };
@@ -935,8 +940,9 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
                     lfill += (long long)acc.size();
                     for (auto &x : acc) growth = std::max(growth, std::fabs(x.second));
                     sc = std::max(sc, scale_of(t));
-                    if (acc.size() > std::max(tail_len_max, (size_t)3 * (size_t)orig_len(t)) ||
-                        (double)(g_fill + lfill) > tail_fill_max * (double)std::max<long long>(g_orig + lorig, 1) + 1024.0) { ok = false; break; }
+                    const double o = (double)std::max<long long>(g_orig + lorig, 1);
+                    const double allowed = std::max(tail_fill_max * o, std::min(tail_fill_cap * o, o + tail_slack * (double)g_levels)) + 1024.0;
+                    if (acc.size() > std::max(tail_len_max, (size_t)3 * (size_t)orig_len(t)) || (double)(g_fill + lfill) > allowed) { ok = false; break; }
                     cand.emplace_back(t, std::move(acc));
                 }
                 if (ok && !(growth <= 1e3 * sc)) ok = false;

@@ -66,12 +66,8 @@ def run(env_extra):
 
 if __name__ == "__main__":
     allres = {}
-    configs = (("cta compact, no chain merging", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_NO_CHAINS": "1"}),
-               ("cta compact, chains of <= 2 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1"}),
-               ("cta compact, chains of <= 4 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "4"}),
-               ("cta compact, chains of <= 8 items", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "8"}),
-               ("cta compact, chains of <= 8 items, fill 16", {"CPK_TEAM": "cta", "CPK_LDL_COMPACT": "1", "CPK_CW_CHAIN_ITEMS": "8", "CPK_CW_CHAIN_FILL": "16"}),
-               ("default", {}))
+    configs = (("default", {"CPK_VERBOSE": "1"}), ("rows <= 768", {"CPK_LDL_TAIL_MAXLEN": "768"}), ("slack 50k", {"CPK_LDL_TAIL_SLACK": "50000"}),
+               ("slack 400k", {"CPK_LDL_TAIL_SLACK": "400000"}))
     if "--quick" in sys.argv:
         configs = (("default", {"CPK_VERBOSE": "1"}),)
     for label, env in configs:
