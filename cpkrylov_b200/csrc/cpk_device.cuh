@@ -177,6 +177,11 @@ struct DevSweep {
     const int    *partner;  // [nitems*32] 2x2 partner row id (F_PARTNER)
     const double *e;        // off-diagonal of the 2x2 block
     const double *dp;       // partner's diagonal entry
+    // rows without any work in either sweep and without dependents (y_i = z_i / d_i): more than half
+    // of the backward rows of a fill-free factor.  One streamed pass instead of items.
+    int nlone;
+    const int    *lone_pidx;    // [nlone] index into the user vector, ascending
+    const double *lone_d;       // [nlone] D(i,i)
 };
 __device__ __forceinline__ int item_slot(const DevSweep &S, int t, int lane)
 {

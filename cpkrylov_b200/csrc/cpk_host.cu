@@ -213,6 +213,9 @@ static cudaError_t upload_sweep(DevArena &ar, const HSweep &h, DevSweep &d)
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    d.nlone = (int)h.lone_pidx.size();
+    if ((e = ar.upload(&d.lone_pidx, h.lone_pidx)) != cudaSuccess) return e;
+    if ((e = ar.upload(&d.lone_d, h.lone_d)) != cudaSuccess) return e;
     d.mptr = nullptr;
     static const bool no_compact_meta = getenv("CPK_LDL_DENSE_META") != nullptr;
     if (h.nitems >= 4096 && h.n_warprow * 4 > (int64_t)h.nitems && !no_compact_meta) {
@@ -1117,6 +1120,22 @@ static int build_sweeps(HostLdl &HL, int N, bool compact_walk, int grid_warps, S
         sweep_append(W, rowsF, p, d, e, partner, grid_warps, entriesF,
                      [&](int r) { return F_FWD | (fused[r] ? F_FUSED : 0); });
         W.nfwd = W.nitems;
+        // lone rows (trivial in the forward sweep, no entry in the backward one; a trivial row has no row
+        // entries, so no backward row gathers its y): a streamed pass of their own instead of items
+        if (!getenv("CPK_LDL_NO_LONE")) {
+            std::vector<SweepRow> keep;
+            std::vector<std::pair<int, double>> lone;
+            keep.reserve(rowsB.size());
+            for (auto &rw : rowsB) {
+                if (triv[rw.row] && rw.len == 0) lone.emplace_back((int)p[rw.row], d[rw.row]);
+                else keep.push_back(rw);
+            }
+            if (lone.size() >= 1024) {
+                std::sort(lone.begin(), lone.end());
+                for (auto &x : lone) { W.lone_pidx.push_back(x.first); W.lone_d.push_back(x.second); }
+                rowsB.swap(keep);
+            }
+        }
         sweep_append(W, rowsB, p, d, e, partner, grid_warps, entriesB,
                      [&](int r) { return (triv[r] ? F_WDIRECT : 0) | (hasR[r] ? F_STORE : 0) | (partner[r] >= 0 ? F_PARTNER : 0); });
     }
@@ -1372,11 +1391,11 @@ extern "C" int cpk_debug_rc(const cpk_csc *A, const cpk_csc *L, const cpk_csc *D
 // debug / test hook (no device needed): the item list of the two sweeps (DevSweep) as build_sweeps
 // compiles it for a grid team -- trivial / fused rows, level merging, warp-rows -- so that a numpy
 // walk can check it against a direct solve.  sizes = {nitems, nfwd, nlev, entries, effective forward
-// levels, effective backward levels, rows rewritten by the merging (fwd), (bwd)}; the arrays may be
+// levels, effective backward levels, rows rewritten by the merging (fwd), (bwd), lone rows}; the arrays may be
 // null (sizes only).
 extern "C" int cpk_debug_sweep(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, int64_t *sizes, int32_t *levptr, int32_t *sptr,
                                int32_t *col, double *val, int32_t *rid, int32_t *pidx, int32_t *flags, double *d, int32_t *partner,
-                               double *e, double *dp)
+                               double *e, double *dp, int32_t *lone_pidx, double *lone_d)
 {
     return guarded([&]() -> int {
         if (!csc_ok(L) || !csc_ok(D) || !perm || !sizes) return fail(CPK_ERR_ARG, "cpk_debug_sweep: bad argument");
@@ -1389,7 +1408,9 @@ extern "C" int cpk_debug_sweep(const cpk_csc *L, const cpk_csc *D, const int64_t
         if (rc) return rc;
         const HSweep &W = SB.W;
         sizes[0] = W.nitems; sizes[1] = W.nfwd; sizes[2] = (int64_t)W.levptr.size(); sizes[3] = (int64_t)W.col.size();
-        sizes[4] = W.lev_f_eff; sizes[5] = W.lev_b_eff; sizes[6] = W.tail_f; sizes[7] = W.tail_b;
+        sizes[4] = W.lev_f_eff; sizes[5] = W.lev_b_eff; sizes[6] = W.tail_f; sizes[7] = W.tail_b; sizes[8] = (int64_t)W.lone_pidx.size();
+        if (lone_pidx) std::copy(W.lone_pidx.begin(), W.lone_pidx.end(), lone_pidx);
+        if (lone_d) std::copy(W.lone_d.begin(), W.lone_d.end(), lone_d);
         if (levptr) { std::copy(W.levptr.begin(), W.levptr.end(), levptr); levptr[W.levptr.size()] = W.nitems; }
         if (sptr) std::copy(W.sptr.begin(), W.sptr.end(), sptr);
         if (col) std::copy(W.col.begin(), W.col.end(), col);

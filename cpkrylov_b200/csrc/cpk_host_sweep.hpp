@@ -14,6 +14,10 @@ struct HSweep {
     int nitems = 0, nfwd = 0;
     std::vector<int> seg, levptr, sptr, col, rid, pidx, flags, partner;
     std::vector<double> val, d, e, dp;
+    // "lone" rows: no work in the forward sweep, no entry in the backward one, gathered by nobody:
+    // y_i = z_i / d_i.  Kept out of the item list: a plain streamed pass (DevSweep::lone_*)
+    std::vector<int> lone_pidx;
+    std::vector<double> lone_d;
     int64_t n_trivial = 0, n_fused = 0, tail_f = 0, tail_b = 0, n_warprow = 0, max_len = 0;
     int lev_f_eff = 0, lev_b_eff = 0;
 };

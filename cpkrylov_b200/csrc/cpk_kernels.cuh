@@ -423,6 +423,29 @@ __device__ __forceinline__ void item_process(Team &T, const DevLdl &M, const Vec
     }
 }
 
+// The lone rows of a solve (DevSweep::lone_*): out[p] = in[p] / d, all loads of four rows per thread in flight.
+// They depend on the input vector only and nobody gathers them: run at the start of a walk, no barrier needed.
+template <class Team>
+__device__ __forceinline__ void ldl_lone_rows(Team &T, const DevSweep &S, const VecIn &in, double *out, bool accumulate)
+{
+    const int nl = S.nlone;
+    const int tid = T.tid, nth = T.nthreads;
+    for (int i0 = tid; i0 < nl; i0 += 4 * nth) {
+        int pi[4]; double dd[4], zz[4], oo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nth;
+            pi[u] = (i < nl) ? __ldg(&S.lone_pidx[i]) : -1;
+            dd[u] = (i < nl) ? __ldg(&S.lone_d[i]) : 1.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { zz[u] = (pi[u] >= 0) ? in(pi[u]) : 0.0; oo[u] = (accumulate && pi[u] >= 0) ? out[pi[u]] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pi[u] >= 0) { const double y = zz[u] / dd[u]; out[pi[u]] = accumulate ? oo[u] + y : y; }
+    }
+}
+
 // Sync-free walk: no barrier inside.  Every produced value is published with
 // the epoch of this solve in one 128-bit store; consumers re-poll until the tag
 // matches.  Items only depend on lower-numbered items, every warp walks its
@@ -433,6 +456,7 @@ __device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const 
 {
     const unsigned long long epoch = (unsigned long long)(unsigned)epoch_i;
     const DevSweep &S = M.sw;
+    ldl_lone_rows(T, S, in, out, accumulate);
     for (int g = 0; g < S.nseg; ++g) {
         const int sbeg = __ldg(&S.seg[3 * g]), send = __ldg(&S.seg[3 * g + 1]), blk = __ldg(&S.seg[3 * g + 2]);
         const int nblk = (send - sbeg + blk - 1) / blk;
@@ -469,8 +493,12 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
     constexpr int B = CPK_SWEEP_B;
     const int Nn = M.N;
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
+    // the lone rows ride on the first BACKWARD level (the lighter one of a shallow sweep: the forward level
+    // holds the long merged rows)
+    bool lone_done = S.nlone == 0;
     for (int g = 0; g < S.nlev; ++g) {
         const int a = __ldg(&S.levptr[g]), b = __ldg(&S.levptr[g + 1]);
+        if (!lone_done && a >= S.nfwd) { ldl_lone_rows(T, S, in, out, accumulate); lone_done = true; }
         const long long cnt = b - a;
         int t = a + (int)(cnt * gwarp / nwarps);
         const int tend = a + (int)(cnt * (gwarp + 1) / nwarps);
@@ -599,6 +627,7 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
         if (g + 1 < S.nlev) T.sync();       // the caller syncs after the last level
         if (dbg) dbg->mark(min(2 * g + 1, 7));
     }
+    if (!lone_done) ldl_lone_rows(T, S, in, out, accumulate);
 }
 
 // ---------------------------------------------------------------------------

@@ -26,23 +26,24 @@ def _sweep(L, d, e, perm):
     fn = lib.cpk_debug_sweep
     fn.restype = ct.c_int
     PC = ct.POINTER(_lib.CscStruct)
-    fn.argtypes = [PC, PC, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)] + [ct.c_void_p] * 11
+    fn.argtypes = [PC, PC, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64)] + [ct.c_void_p] * 13
     N = d.size
     Dm = sp.diags([d, e[:-1], e[:-1]], [0, -1, 1], shape=(N, N), format="csc")
     Lc, Dc = _lib.Csc(L), _lib.Csc(Dm)
     perm = np.ascontiguousarray(perm, dtype=np.int64)
-    sizes = np.zeros(8, dtype=np.int64)
+    sizes = np.zeros(9, dtype=np.int64)
     pp = perm.ctypes.data_as(ct.POINTER(ct.c_int64))
     ps = sizes.ctypes.data_as(ct.POINTER(ct.c_int64))
-    _lib.check(fn(Lc.ref(), Dc.ref(), pp, ps, *([None] * 11)))
+    _lib.check(fn(Lc.ref(), Dc.ref(), pp, ps, *([None] * 13)))
     nitems, nfwd, nlev, nent = (int(v) for v in sizes[:4])
     i32 = lambda n: np.zeros(max(n, 1), dtype=np.int32)
     f64 = lambda n: np.zeros(max(n, 1))
     S = dict(nitems=nitems, nfwd=nfwd, nlev=nlev, lev_f=int(sizes[4]), lev_b=int(sizes[5]), merged_f=int(sizes[6]), merged_b=int(sizes[7]),
              levptr=i32(nlev + 1), sptr=i32(nitems + 1), col=i32(nent), val=f64(nent), rid=i32(nitems * 32), pidx=i32(nitems * 32),
-             flags=i32(nitems * 32), d=f64(nitems * 32), partner=i32(nitems * 32), e=f64(nitems * 32), dp=f64(nitems * 32))
+             flags=i32(nitems * 32), d=f64(nitems * 32), partner=i32(nitems * 32), e=f64(nitems * 32), dp=f64(nitems * 32),
+             nlone=int(sizes[8]), lone_pidx=i32(int(sizes[8])), lone_d=f64(int(sizes[8])))
     _lib.check(fn(Lc.ref(), Dc.ref(), pp, ps, *[S[k].ctypes.data for k in
-                                                 ("levptr", "sptr", "col", "val", "rid", "pidx", "flags", "d", "partner", "e", "dp")]))
+                                                 ("levptr", "sptr", "col", "val", "rid", "pidx", "flags", "d", "partner", "e", "dp", "lone_pidx", "lone_d")]))
     return S
 
 
@@ -53,6 +54,10 @@ def _walk(S, N, z):
     out = np.full(N, np.nan)
     nwritten = np.zeros(N, dtype=np.int64)
     lanes = np.arange(32)
+    # lone rows (ldl_lone_rows): y = z / d straight from the input vector
+    lp = S["lone_pidx"][:S["nlone"]]
+    out[lp] = z[lp] / S["lone_d"][:S["nlone"]]
+    nwritten[lp] += 1
     for g in range(S["nlev"]):
         a, b = int(S["levptr"][g]), int(S["levptr"][g + 1])
         w_new, y_new = {}, {}
