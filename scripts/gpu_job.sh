@@ -1,23 +1,15 @@
 mkdir -p gpurun_out
-exp() { ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1.raw.csv 2>/dev/null; ncu -i gpurun_out/$1.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/$1.source.csv.gz; [ "$2" = keep ] || rm -f gpurun_out/$1.ncu-rep; }
-B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-parts --no-parity"
-$B --profile > gpurun_out/r2_bench_profile.json 2> gpurun_out/r2_bench_profile.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $B > gpurun_out/r2_ncu1.log 2>&1
-$B > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_solve -s 3 -c 1 -f -o gpurun_out/r2_k_solve_cpcg $B > gpurun_out/r2_ncu2.log 2>&1
-exp r2_k_solve_cpcg
-K="python scripts/kernel_bench.py --reps 12"
-$K > gpurun_out/r2_kernel_bench.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_matvec -s 6 -c 1 -f -o gpurun_out/r2_k_matvec_H $K > gpurun_out/r2_ncu3.log 2>&1
-exp r2_k_matvec_H
-$K > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_apply -s 6 -c 1 -f -o gpurun_out/r2_k_apply_nitref0 $K > gpurun_out/r2_ncu4.log 2>&1
-exp r2_k_apply_nitref0
-$K > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_apply -s 18 -c 1 -f -o gpurun_out/r2_k_apply_default $K > gpurun_out/r2_ncu5.log 2>&1
-exp r2_k_apply_default
-S="python bench.py --g 60 --k 6 --window 64 --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-parts --no-parity"
-$S > gpurun_out/r2_bench_stress60.json 2>/dev/null && \
-ncu --set full --clock-control none --import-source on -k regex:k_solve -s 3 -c 1 -f -o gpurun_out/r2_k_solve_stress60 $S > gpurun_out/r2_ncu6.log 2>&1
-exp r2_k_solve_stress60
-du -sh gpurun_out; tail -2 gpurun_out/r2_kernel_bench.log | cut -c1-500
+: > gpurun_out/r2_ab44.log
+for rep in 1 2; do
+for lib in prev mixed; do
+export CPK_LIB_PATH=$PWD/cpkrylov_b200/libcpk_$lib.so
+python bench.py --no-cpu-baseline --no-parts --no-parity --no-extras --steps 30 2>&1 | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); c=d['config']
+print('$lib cfg3 ms/solve %.4f frac %.3f' % (c['device_ms_per_step'], d['roofline']['frac']))" | tee -a gpurun_out/r2_ab44.log
+python bench.py --workload kkt_convdiff --no-cpu-baseline --no-parts --no-parity --no-extras --steps 6 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); c=d['config']
+print('$lib cfg4 ms/solve %.3f frac %.3f' % (c['device_ms_per_step'], d['roofline']['frac']))" | tee -a gpurun_out/r2_ab44.log
+done
+done
