@@ -71,7 +71,7 @@ static uint64_t pattern_hash(const cpk_csc *A)
 // device objects
 // ===========================================================================
 #include "cpk_host_compact.hpp"
-constexpr int kRcSweepMaxW = 32;    // same for the rows of a sweep (tail inversion makes rows of tens of entries)
+constexpr int kRcSweepMaxW = 32;    // same for the rows of a sweep (level merging makes rows of tens of entries)
 constexpr int kRcMatMaxW = 16;      // widest row class of a plain matrix in row-class form (wider rows: one warp per row)
 
 // Device memory of one object.  Arrays come from the device's stream-ordered pool
@@ -470,13 +470,11 @@ static bool use_grid(int N)
 }
 
 // Team of a SINGLE-system launch.  Measured per-iteration times (cpminres, example options,
-// kkt_lap3d patterns, `scripts/team_crossover.py`):
-//   shallow sweeps (k=2, tail inversion collapses them):  grid flat ~50 us for N = 1 250 .. 24 600;
-//     one CTA 38 / 54 / 94 / 138 / 205 / 295 / 595 us at N = 1 250 / 2 160 / 4 218 / 7 290 / 11 576 / 17 280 / 24 603
-//   deep sweeps (k=6 windowed, 182 / 268 / 514 levels): one CTA with the compact walk 235 / 469 / 1 029 us,
-//     grid (sync-free walk) 932 / 1 376 / 2 633 us
-// i.e. one CTA ~ 20 + 0.016 N (+ 1.2 per level when the compact walk is needed), grid ~ 55 for sweeps
-// the tail inversion flattens (<= 48 levels here) and ~ 50 + 5 per level otherwise.
+// kkt_lap3d patterns, `scripts/team_crossover.py`, round-2 build with level merging):
+//   shallow sweeps (k=2, merged to 1+1 levels):  grid flat 58-66 us for N = 1 250 .. 24 600;
+//     one CTA 44 / 53 / 82 / 116 / 194 / 284 / 420 us at N = 1 250 / 2 160 / 4 218 / 7 290 / 11 576 / 17 280 / 24 603
+//   deep factors (k=6 windowed, 91 / 134 / 257 levels per sweep): one CTA with the compact walk 206 / 459 / 997 us,
+//     grid over the merged sweeps 101 / 140 / 246 us (round 1, unmerged sync-free walk: 932 / 1 376 / 2 633 us)
 // Batches keep the size rule (use_grid): there one SM per system is the point.
 // Cost model of one iteration (two LDL' solves), us, fitted to measurements on the example systems and the
 // kkt_lap3d family (`scripts/compact_probe.py`, `scripts/team_crossover.py`):
@@ -825,7 +823,7 @@ static int parse_ldl(const cpk_csc *L, const cpk_csc *D, const int64_t *perm, in
 
 // ---------------------------------------------------------------------------
 // The two sweeps of the LDL' solve, compiled from the parsed factors: row classification
-// (trivial / fused rows), tail inversion, then the item list (level / sync-free walks) and/or
+// (trivial / fused rows), level merging, then the item list (level / sync-free walks) and/or
 // the row-class form (shallow sweeps with a diagonal D).  No device needed.
 // ---------------------------------------------------------------------------
 // substituted rows of the level merging, by LDL row (a dense table: hash maps of a million

@@ -84,7 +84,7 @@ def test_ldl_walk_variants_agree(cp, env, team):
     list, row-class passes for shallow sweeps with a diagonal D -- CPK_LDL_RC=1 --, and the
     shared-memory compact walk of the one-CTA team) and
     setup shortcuts (trivial/fused
-    rows, tail inversion); every combination must give the oracle's answer (the
+    rows, level merging); every combination must give the oracle's answer (the
     switches are read when the operator is created).  The global-memory walks of the
     one-CTA team are reached with CPK_LDL_COMPACT=0; CPK_LDL_COMPACT=1 forces the
     compact walk on the shallow cvxqp2 factor as well."""
