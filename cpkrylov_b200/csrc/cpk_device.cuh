@@ -182,6 +182,12 @@ struct DevSweep {
     int nlone;
     const int    *lone_pidx;    // [nlone] index into the user vector, ascending
     const double *lone_d;       // [nlone] D(i,i)
+    // Level walk: the items of a level are cut into one contiguous share per CTA, balanced by estimated
+    // COST (a generic item costs several batched ones), and the warps of a CTA take batches off the share
+    // through a shared-memory counter.  ctasplit [nlev][nsplit+1] = first item of every CTA's share;
+    // used when the team has exactly nsplit CTAs (otherwise: equal item counts per CTA).
+    int nsplit;
+    const int    *ctasplit;
 };
 __device__ __forceinline__ int item_slot(const DevSweep &S, int t, int lane)
 {
@@ -423,6 +429,7 @@ constexpr long long kWatchdogCycles = 4000000000LL;   // ~2 s of SM clocks
 struct TeamShared {
     double red[kWarpsPerCta][kRedMax];
     double out[kRedMax];
+    int wq[2];              // work queues of the level walk (items of the CTA's share handed out in batches)
 };
 
 struct GridTeam {
@@ -456,6 +463,8 @@ struct GridTeam {
     __device__ __forceinline__ bool leader() const { return tid == 0; }
     __device__ __forceinline__ bool cta_leader() const { return threadIdx.x == 0; }
     __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+    __device__ __forceinline__ int cta() const { return bid; }
+    __device__ __forceinline__ int nctas() const { return nblk; }
 
     __device__ void sync() {
         __syncthreads();
@@ -583,6 +592,8 @@ struct CtaTeam {
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ bool cta_leader() const { return threadIdx.x == 0; }
     __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+    __device__ __forceinline__ int cta() const { return 0; }
+    __device__ __forceinline__ int nctas() const { return 1; }
 
     template <int K>
     __device__ void wide_store(double (&v)[K], int col0, int nvalid, double *dst /*shared*/) {

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <mutex>
 #include <numeric>
+#include <queue>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -213,6 +214,10 @@ static cudaError_t upload_sweep(DevArena &ar, const HSweep &h, DevSweep &d)
     if ((e = ar.upload(&d.sptr, h.sptr)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.col, h.col)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.val, h.val)) != cudaSuccess) return e;
+    d.nsplit = h.nsplit;
+    d.ctasplit = nullptr;
+    if (h.ctasplit.size() == (size_t)(h.nsplit + 1) * h.levptr.size() && h.nsplit > 1)
+        if ((e = ar.upload(&d.ctasplit, h.ctasplit)) != cudaSuccess) return e;
     d.nlone = (int)h.lone_pidx.size();
     if ((e = ar.upload(&d.lone_pidx, h.lone_pidx)) != cudaSuccess) return e;
     if ((e = ar.upload(&d.lone_d, h.lone_d)) != cudaSuccess) return e;

@@ -18,6 +18,9 @@ struct HSweep {
     // y_i = z_i / d_i.  Kept out of the item list: a plain streamed pass (DevSweep::lone_*)
     std::vector<int> lone_pidx;
     std::vector<double> lone_d;
+    // level walk: first item of every CTA's share of every level ([levels][nsplit+1], see DevSweep)
+    int nsplit = 0;
+    std::vector<int> ctasplit;
     int64_t n_trivial = 0, n_fused = 0, tail_f = 0, tail_b = 0, n_warprow = 0, max_len = 0;
     int lev_f_eff = 0, lev_b_eff = 0;
 };
@@ -28,11 +31,97 @@ typedef std::vector<std::pair<int, double>> EncRow;     // (column code, value),
 
 // Appends the rows (already filtered) of one direction.  `entries(r)` returns the
 // encoded dependency list of LDL row r.
-// Items of a level are created sorted by cost (long rows first).  Deal them
-// round-robin to the `nw` warps that will walk the level and store every
-// warp's hand contiguously: each warp still streams a contiguous range, and
-// every range holds the same mix of expensive and cheap items.
-static void deal_level(HSweep &W, int first, int n, int nw)
+// The items of a level are then DEALT to the CTAs that will walk it: every CTA gets one contiguous
+// share, balanced by the estimated cost of the items (longest-processing-time-first), and inside a share
+// the items are ordered by kind, so that the batches the warps draw from it are of one kind.  Cost in
+// dependent round trips: a lane item of <= 2 entries per row or a warp-row of <= 64 entries is walked
+// in batches of two (3 trips per batch), anything else item by item (3 trips + 2 per chunk of
+// 4 entries per lane).
+static int item_kind(const HSweep &W, int it)
+{
+    const int width = (W.sptr[it + 1] - W.sptr[it]) / 32;
+    const int f0 = W.flags[(size_t)it * 32];
+    bool partner = false;
+    for (int l = 0; l < 32; ++l) partner = partner || (W.flags[(size_t)it * 32 + l] & F_PARTNER);
+    if (partner) return 2;
+    if (f0 & F_WARPROW) return width <= 2 ? 1 : 2;
+    return width <= 2 ? 0 : 2;
+}
+static int item_cost(const HSweep &W, int it)
+{
+    const int width = (W.sptr[it + 1] - W.sptr[it]) / 32;
+    return item_kind(W, it) == 2 ? 6 + 4 * ((std::max(width, 1) + 3) / 4) : 3;     // in half round trips
+}
+static void deal_level(HSweep &W, int first, int n, int nctas)
+{
+    std::vector<int> order;             // new position -> old item (relative)
+    order.reserve(n);
+    std::vector<int> split((size_t)nctas + 1, first);
+    if (n > 0) {
+        std::vector<int> kind(n), cost(n), idx(n);
+        for (int i = 0; i < n; ++i) { kind[i] = item_kind(W, first + i); cost[i] = item_cost(W, first + i); idx[i] = i; }
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        std::vector<std::vector<int>> share(nctas);
+        typedef std::pair<long long, int> Load;     // (cost so far, CTA)
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int c = 0; c < nctas; ++c) heap.push(Load(0, c));
+        for (int i : idx) {
+            Load l = heap.top(); heap.pop();
+            share[l.second].push_back(i);
+            heap.push(Load(l.first + cost[i], l.second));
+        }
+        for (int c = 0; c < nctas; ++c) {
+            // generic items first (the long poles), then warp-rows, then lane items; original order inside a kind
+            // (rows of equal length are ordered by their index in the user vector: coalesced gathers)
+            std::stable_sort(share[c].begin(), share[c].end(), [&](int x, int y) {
+                const int kx = kind[x] == 2 ? 0 : kind[x] == 1 ? 1 : 2, ky = kind[y] == 2 ? 0 : kind[y] == 1 ? 1 : 2;
+                if (kx != ky) return kx < ky;
+                return x < y;
+            });
+            split[c] = first + (int)order.size();
+            for (int i : share[c]) order.push_back(i);
+        }
+        split[nctas] = first + n;
+    }
+    W.ctasplit.insert(W.ctasplit.end(), split.begin(), split.end());
+    if (n <= 1) return;
+    // rebuild the item arrays of this level in the new order
+    const int s0 = W.sptr[first];
+    std::vector<int> col, sptr(1, s0), rid, pidx, flags, partner;
+    std::vector<double> val, d, e, dp;
+    {
+        const size_t ne = (size_t)(W.sptr[first + n] - s0), ns = (size_t)n * 32;
+        col.reserve(ne); val.reserve(ne); sptr.reserve((size_t)n + 1);
+        rid.reserve(ns); pidx.reserve(ns); flags.reserve(ns); partner.reserve(ns); d.reserve(ns); e.reserve(ns); dp.reserve(ns);
+    }
+    for (int k = 0; k < n; ++k) {
+        const int it = first + order[k];
+        const int b = W.sptr[it], en = W.sptr[it + 1];
+        col.insert(col.end(), W.col.begin() + b, W.col.begin() + en);
+        val.insert(val.end(), W.val.begin() + b, W.val.begin() + en);
+        sptr.push_back(s0 + (int)col.size());
+        for (int l = 0; l < 32; ++l) {
+            const size_t sl = (size_t)it * 32 + l;
+            rid.push_back(W.rid[sl]); pidx.push_back(W.pidx[sl]); flags.push_back(W.flags[sl]); partner.push_back(W.partner[sl]);
+            d.push_back(W.d[sl]); e.push_back(W.e[sl]); dp.push_back(W.dp[sl]);
+        }
+    }
+    std::copy(col.begin(), col.end(), W.col.begin() + s0);
+    std::copy(val.begin(), val.end(), W.val.begin() + s0);
+    for (int k = 0; k <= n; ++k) W.sptr[first + k] = sptr[k];
+    const size_t base = (size_t)first * 32;
+    std::copy(rid.begin(), rid.end(), W.rid.begin() + base);
+    std::copy(pidx.begin(), pidx.end(), W.pidx.begin() + base);
+    std::copy(flags.begin(), flags.end(), W.flags.begin() + base);
+    std::copy(partner.begin(), partner.end(), W.partner.begin() + base);
+    std::copy(d.begin(), d.end(), W.d.begin() + base);
+    std::copy(e.begin(), e.end(), W.e.begin() + base);
+    std::copy(dp.begin(), dp.end(), W.dp.begin() + base);
+}
+
+// Small systems (one CTA, or a grid that holds a warp per item): every warp owns a contiguous range of equal
+// COUNT; the items, sorted by cost, are dealt round-robin to the warps, so every range holds the same mix.
+static void deal_level_rr(HSweep &W, int first, int n, int nw)
 {
     if (n <= 1 || nw <= 1) return;
     std::vector<int> order;             // new position -> old item (relative)
@@ -91,7 +180,14 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
                          int grid_warps, Entries entries, Flags flags_of)
 {
     // the team shape that will walk this system: whole grid for large N, one CTA otherwise
-    const int deal_warps = (int)perm.size() > 24576 ? grid_warps : kWarpsPerCta;
+    // shares per CTA + work queue: large systems with SHALLOW sweeps (cfg 3 / cfg 4: 1+1 levels of tens of
+    // thousands of items; cfg 3 solve 3.31 -> 3.16 ms, batches of N = 80 000 systems on sub-teams 3.84 -> 3.40 ms).
+    // Sweeps of many small levels keep the round-robin deal: measured 8-10 % slower with shares (stress g=40,
+    // 16+2 levels), and the sync-free walk of deep sweeps hands consecutive items to a warp anyway.
+    const bool large = (int)perm.size() > 24576;
+    const bool big = large && W.lev_f_eff + W.lev_b_eff <= 4;
+    const int deal_ctas = big ? std::max(grid_warps / kWarpsPerCta, 1) : 0;      // 0: equal counts per warp (deal_level_rr)
+    W.nsplit = deal_ctas;
     // inside a level any order is valid: group rows of equal (short) length and
     // order them by their index in the user vector, so that the P' gather and the
     // P scatter of consecutive lanes touch consecutive addresses
@@ -188,7 +284,8 @@ static void sweep_append(HSweep &W, std::vector<SweepRow> rows, const std::vecto
         }
         level_items.emplace_back(first_item, W.nitems - first_item);
         W.levptr.push_back(first_item);
-        deal_level(W, first_item, W.nitems - first_item, deal_warps);
+        if (big) deal_level(W, first_item, W.nitems - first_item, deal_ctas);
+        else deal_level_rr(W, first_item, W.nitems - first_item, large ? grid_warps : kWarpsPerCta);
     }
     // segments: a level with at least 2 items per warp is "bulk" (blocks of
     // consecutive items per warp); runs of smaller levels

@@ -482,9 +482,9 @@ __device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const 
 // memory round trips per batch instead of three per item.  Items that are not
 // "simple" (rows longer than 2 entries, warp-rows, 2x2 pivots) take the generic
 // per-item path.
-template <class Team>
-__device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
-                                              PhaseClock *dbg = nullptr)
+template <bool DYN, class Team>
+__device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
+                                                   PhaseClock *dbg)
 {
     const DevSweep &S = M.sw;
 #ifndef CPK_SWEEP_B
@@ -496,12 +496,40 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
     // the lone rows ride on the first BACKWARD level (the lighter one of a shallow sweep: the forward level
     // holds the long merged rows)
     bool lone_done = S.nlone == 0;
+    // every CTA walks ITS share of a level (cost-balanced at set-up); inside the CTA the warps take
+    // batches off the share through a counter in shared memory, so a warp that drew cheap items simply
+    // draws more of them.  Two counters, used alternately: the one of the next level is reset while this
+    // level runs (the team barrier between the levels orders the reset before its first use).
+    const int cta = T.cta(), nctas = T.nctas();
+    constexpr bool dyn = DYN;                     // large shallow systems (S.ctasplit); otherwise: a contiguous range of equal count per warp
+    const bool exact = dyn && S.nsplit == nctas;   // the shares were cut for this team shape (else: equal counts per CTA)
+    int *wq = T.sh->wq;
+    if (dyn) {
+        if (threadIdx.x == 0) { wq[0] = 0; wq[1] = 0; }
+        T.cta_sync();
+    }
     for (int g = 0; g < S.nlev; ++g) {
         const int a = __ldg(&S.levptr[g]), b = __ldg(&S.levptr[g + 1]);
         if (!lone_done && a >= S.nfwd) { ldl_lone_rows(T, S, in, out, accumulate); lone_done = true; }
         const long long cnt = b - a;
-        int t = a + (int)(cnt * gwarp / nwarps);
-        const int tend = a + (int)(cnt * (gwarp + 1) / nwarps);
+        int t, tend, cs = 0;
+        int *queue = &wq[g & 1];
+        if (dyn) {
+            if (exact) {
+                cs = __ldg(&S.ctasplit[(size_t)g * (nctas + 1) + cta]);
+                tend = __ldg(&S.ctasplit[(size_t)g * (nctas + 1) + cta + 1]);
+            } else {
+                cs = a + (int)(cnt * cta / nctas);
+                tend = a + (int)(cnt * (cta + 1) / nctas);
+            }
+            if (threadIdx.x == 0) wq[(g + 1) & 1] = 0;
+            t = 0;
+            if (lane == 0) t = atomicAdd(queue, B);
+            t = __shfl_sync(FULL, t, 0) + cs;
+        } else {
+            t = a + (int)(cnt * gwarp / nwarps);
+            tend = a + (int)(cnt * (gwarp + 1) / nwarps);
+        }
         while (t < tend) {
             const int nb = min(B, tend - t);
             // ---- stage A: row data of the whole batch -------------------------------
@@ -621,13 +649,25 @@ __device__ __noinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const Ve
                     }
                 }
             }
-            t += nb;
+            if (dyn) {
+                int tn = 0;
+                if (lane == 0) tn = atomicAdd(queue, B);
+                t = __shfl_sync(FULL, tn, 0) + cs;
+            } else t += nb;
         }
         if (dbg) dbg->mark(min(2 * g, 6));
         if (g + 1 < S.nlev) T.sync();       // the caller syncs after the last level
         if (dbg) dbg->mark(min(2 * g + 1, 7));
     }
     if (!lone_done) ldl_lone_rows(T, S, in, out, accumulate);
+}
+
+template <class Team>
+__device__ __forceinline__ void ldl_solve_levels(Team &T, const DevLdl &M, const VecIn in, double *out, bool accumulate,
+                                                 PhaseClock *dbg = nullptr)
+{
+    if (M.sw.ctasplit != nullptr) ldl_solve_levels_impl<true>(T, M, in, out, accumulate, dbg);
+    else ldl_solve_levels_impl<false>(T, M, in, out, accumulate, dbg);
 }
 
 // ---------------------------------------------------------------------------
