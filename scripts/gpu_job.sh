@@ -1,17 +1,19 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
-: > gpurun_out/r2_ab51.log
-for lib in prev queue; do
-export CPK_LIB_PATH=$PWD/cpkrylov_b200/libcpk_$lib.so
-python bench.py --no-cpu-baseline --no-parts --no-parity --no-extras --steps 30 2>&1 | tail -1 | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); c=d['config']
-print('$lib cfg3 ms/solve %.4f frac %.3f' % (c['device_ms_per_step'], d['roofline']['frac']))" | tee -a gpurun_out/r2_ab51.log
-timeout 600 python scripts/compact_probe.py --quick 2>&1 | grep "us_per_iter" | head -4 | tr '\n' ' ' | sed "s/^/$lib fixtures /" | tee -a gpurun_out/r2_ab51.log; echo
-python scripts/subteam_probe.py 2>&1 | head -3 | sed "s/^/$lib /" | tee -a gpurun_out/r2_ab51.log
-env A=1 timeout 400 python scripts/stress_env_probe.py 40 "$lib g40" 2>&1 | tail -1 | tee -a gpurun_out/r2_ab51.log
-python bench.py --workload ipm_batch --steps 5 --warmup 3 2>&1 | tail -1 | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); c=d['config']
-print('$lib cfg5 device ms/step %.3f' % c['device_ms_per_step'])" | tee -a gpurun_out/r2_ab51.log
-done
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_pytest52.log
+python bench.py > gpurun_out/r2_bench52.json 2> gpurun_out/r2_bench52.err; tail -2 gpurun_out/r2_bench52.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench52.json').read().strip().splitlines()[-1])
+c=d['config']
+print('cfg3 ms/solve %.4f it/s %d e2e %d frac %.3f setup_s %.2f'%(c['device_ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], c['setup_s']))
+for k,v in d['roofline_parts'].items(): print(' ',k,'us %.1f frac %.3f'%(v['us'],v['frac']))
+b=d['cfg5_ipm_batch']; print('cfg5', b['value'], b['ms_per_step'], b['config']['device_ms_per_step'])
+s=d['stress_k6']; print('stress', s['ms_per_step'], s['roofline']['frac'], s['config']['setup_s'], s['parity']['relerr_vs_oracle'])
+print('parity', d['parity'])
+PY
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+CPK_RESULTS_TAG=r2 timeout 1500 python scripts/results_table.py 2>&1 | grep "^{" > gpurun_out/r2_results52.log; python - <<'PY'
+import json
+for l in open('gpurun_out/r2_results52.log'):
+    r=json.loads(l); print(r['config'][:4], r['solver'], {k:v for k,v in r.get('opts',{}).items() if k not in ('atol','rtol','itmax','force_itref')}, 'iters', r.get('iters'), 'ms %.3f'%r.get('ms',0), 'it/s %d'%r.get('it_per_s',0), 'GBs %d'%r.get('GBs',0), 'frac %.3f'%r.get('frac',0))
+PY
