@@ -27,6 +27,40 @@ constexpr int CPK_PH_SPMV_ = 0, CPK_PH_LDL_ = 1, CPK_PH_RESID_ = 2, CPK_PH_VEC_ 
 constexpr int CPK_ERR_INDEFINITE_ = -5, CPK_ERR_BREAKDOWN_ = -6, CPK_ERR_TIMEOUT_ = -7;
 
 // ---------------------------------------------------------------------------
+// Cache hints.  A cfg-3 iteration streams ~130 MB of matrix and item arrays past ~60 MB of Krylov
+// vectors that the NEXT phase gathers from; with plain loads the streams push the vectors out of
+// the L2 and every gather round trip goes to DRAM.
+//   ld_stream  streamed, read-once-per-pass arrays (entries, row maps, item data): ld.global.cs,
+//              evict-first in L1 and L2 (CPK_STREAM_HINT=0: ld.global.nc)
+//   ld_keep    a matrix small enough to survive from one iteration to the next (packed stencil
+//              entries of H, 4 bytes per entry): ld.global.nc, normal priority
+//   st_tmp / ld_tmp   sweep intermediates (w of the forward sweep, y of the backward sweep):
+//              written once, read once by the next level (CPK_TMP_HINT=0: plain accesses)
+// Measured on cfg 3 (profiles/r2_notes.md, "cache hints"): 3.164 -> 3.03 ms per solve together
+// with the lazy residual vector; an evict-last policy on H, evict-first on H, and evict-first
+// loads of vectors at their last use were each slower.
+// ---------------------------------------------------------------------------
+#ifndef CPK_STREAM_HINT
+#define CPK_STREAM_HINT 1
+#endif
+#if CPK_STREAM_HINT
+template <class V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
+#else
+template <class V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldg(p); }
+#endif
+template <class V> __device__ __forceinline__ V ld_keep(const V *p) { return __ldg(p); }
+#ifndef CPK_TMP_HINT
+#define CPK_TMP_HINT 1
+#endif
+#if CPK_TMP_HINT
+__device__ __forceinline__ void st_tmp(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ double ld_tmp(const double *p) { return __ldcs(p); }
+#else
+__device__ __forceinline__ void st_tmp(double *p, double v) { *p = v; }
+__device__ __forceinline__ double ld_tmp(const double *p) { return *p; }
+#endif
+
+// ---------------------------------------------------------------------------
 // matrices
 // ---------------------------------------------------------------------------
 // SELL-32 (sliced ELLPACK, slice height = warp) with a per-lane row map, plus a
@@ -654,7 +688,15 @@ struct CtaTeam {
 #define CPK_TEAM_MAP_B 1
 #endif
 constexpr int kTmB = CPK_TEAM_MAP_B;    // batches of loads a thread has in flight in team_map
-template <int NIN, class Team, class Body>
+// CS: bit k set = source k is dead after this pass (CPK_DEAD_HINT: loaded evict-first, so that it
+// leaves the L2 before the vectors the next phase gathers from)
+#ifndef CPK_DEAD_HINT
+#define CPK_DEAD_HINT 1
+#endif
+__device__ __forceinline__ double2 ld_dead(const double2 *p) { return CPK_DEAD_HINT ? __ldcs(p) : *p; }
+__device__ __forceinline__ double ld_dead(const double *p) { return CPK_DEAD_HINT ? __ldcs(p) : *p; }
+__device__ __forceinline__ void st_dead(double *p, double v) { if (CPK_DEAD_HINT) __stcs(p, v); else *p = v; }
+template <int NIN, unsigned CS = 0u, class Team, class Body>
 __device__ __forceinline__ void team_map(const Team &T, int N, const double *const (&src)[NIN], Body &&body)
 {
     const int nt = T.nthreads;
@@ -674,7 +716,9 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
                 const int j = j0 + u * nt;
                 if (j < N2) {
 #pragma unroll
-                    for (int k = 0; k < NIN; ++k) v[u][k] = reinterpret_cast<const double2 *>(src[k])[j];
+                    for (int k = 0; k < NIN; ++k)
+                        v[u][k] = ((CS >> k) & 1u) ? ld_dead(reinterpret_cast<const double2 *>(src[k]) + j)
+                                                   : reinterpret_cast<const double2 *>(src[k])[j];
                 }
             }
 #pragma unroll
@@ -697,7 +741,7 @@ __device__ __forceinline__ void team_map(const Team &T, int N, const double *con
                 const int i = i0 + u * nt;
                 if (i < N) {
 #pragma unroll
-                    for (int k = 0; k < NIN; ++k) v[u][k] = src[k][i];
+                    for (int k = 0; k < NIN; ++k) v[u][k] = ((CS >> k) & 1u) ? ld_dead(&src[k][i]) : src[k][i];
                 }
             }
 #pragma unroll

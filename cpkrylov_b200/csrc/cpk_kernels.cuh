@@ -35,6 +35,9 @@ struct PhaseClock {
 // the row of its lane, i.e. the slice the entry belongs to: a decode cursor runs over the chunk
 // ahead of the accumulating cursor (slice ends and row maps are one slice ahead in registers
 // either way).
+#ifndef CPK_LAZY_RVEC
+#define CPK_LAZY_RVEC 1
+#endif
 #ifndef CPK_SPMV_UP
 #define CPK_SPMV_UP 8
 #endif
@@ -46,7 +49,7 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
     {
         const int *split = A.wsplit[Team::kKind];
         if (split != nullptr && A.nws[Team::kKind] == nwarps) {
-            sa = __ldg(&split[gwarp]); sb = __ldg(&split[gwarp + 1]);
+            sa = ld_keep(&split[gwarp]); sb = ld_keep(&split[gwarp + 1]);
         } else {
             sa = (int)((long long)A.nslices * gwarp / nwarps);
             sb = (int)((long long)A.nslices * (gwarp + 1) / nwarps);
@@ -54,19 +57,19 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
     }
     if (sa < sb) {
         int s = sa;
-        int k = __ldg(&A.sptr[sa]);
-        const int kb = __ldg(&A.sptr[sb]);
-        int send = __ldg(&A.sptr[s + 1]);
-        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-        int row = __ldg(&A.rowmap[s * 32 + lane]);
-        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+        int k = ld_keep(&A.sptr[sa]);
+        const int kb = ld_keep(&A.sptr[sb]);
+        int send = ld_keep(&A.sptr[s + 1]);
+        int send2 = (s + 2 <= sb) ? ld_keep(&A.sptr[s + 2]) : kb;
+        int row = ld_keep(&A.rowmap[s * 32 + lane]);
+        int row2 = (s + 1 < sb) ? ld_keep(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
         constexpr int U = CPK_SPMV_UP;
         unsigned ee[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int kk = k + 32 * u + lane;
-            ee[u] = (kk < kb) ? __ldg(&A.pk[kk]) : 0u;
+            ee[u] = (kk < kb) ? ld_keep(&A.pk[kk]) : 0u;
         }
         while (k < kb) {
             unsigned en[U];
@@ -75,7 +78,7 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int kk = k2 + 32 * u + lane;
-                en[u] = (kk < kb) ? __ldg(&A.pk[kk]) : 0u;
+                en[u] = (kk < kb) ? ld_keep(&A.pk[kk]) : 0u;
             }
             // decode: row of every entry of the chunk (a chunk seldom crosses more than one slice end)
             {
@@ -86,8 +89,8 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
                     if (k0 < kb) {
                         while (k0 >= sendd) {
                             ++sd; sendd = send2d; rowd = row2d;
-                            send2d = (sd + 2 <= sb) ? __ldg(&A.sptr[sd + 2]) : kb;
-                            row2d = (sd + 1 < sb) ? __ldg(&A.rowmap[(sd + 1) * 32 + lane]) : -1;
+                            send2d = (sd + 2 <= sb) ? ld_keep(&A.sptr[sd + 2]) : kb;
+                            row2d = (sd + 1 < sb) ? ld_keep(&A.rowmap[(sd + 1) * 32 + lane]) : -1;
                         }
                         const int col = max(rowd, 0) + (int)(short)(ee[u] & 0xffffu);
                         xv[u] = x[col];
@@ -103,8 +106,8 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
                         if (row >= 0) epi(row, acc);
                         acc = 0.0; ++s;
                         send = send2; row = row2;
-                        send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+                        send2 = (s + 2 <= sb) ? ld_keep(&A.sptr[s + 2]) : kb;
+                        row2 = (s + 1 < sb) ? ld_keep(&A.rowmap[(s + 1) * 32 + lane]) : -1;
                     }
                     acc += vv[u] * xv[u];
                 }
@@ -117,16 +120,16 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
             if (row >= 0) epi(row, acc);
             acc = 0.0; ++s;
             row = row2;
-            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+            row2 = (s + 1 < sb) ? ld_keep(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         }
     }
     for (int r = gwarp; r < A.nlong; r += nwarps) {
-        const int beg = __ldg(&A.lptr[r]), end = __ldg(&A.lptr[r + 1]);
+        const int beg = ld_keep(&A.lptr[r]), end = ld_keep(&A.lptr[r + 1]);
         double acc = 0.0;
-        for (int kk = beg + lane; kk < end; kk += 32) acc += __ldg(&A.lval[kk]) * x[__ldg(&A.lcol[kk])];
+        for (int kk = beg + lane; kk < end; kk += 32) acc += ld_keep(&A.lval[kk]) * x[ld_keep(&A.lcol[kk])];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (lane == 0) epi(__ldg(&A.lrow[r]), acc);
+        if (lane == 0) epi(ld_keep(&A.lrow[r]), acc);
     }
 }
 
@@ -144,7 +147,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
     {
         const int *split = A.wsplit[Team::kKind];
         if (split != nullptr && A.nws[Team::kKind] == nwarps) {
-            sa = __ldg(&split[gwarp]); sb = __ldg(&split[gwarp + 1]);
+            sa = ld_stream(&split[gwarp]); sb = ld_stream(&split[gwarp + 1]);
         } else {
             sa = (int)((long long)A.nslices * gwarp / nwarps);
             sb = (int)((long long)A.nslices * (gwarp + 1) / nwarps);
@@ -152,12 +155,12 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
     }
     if (sa < sb) {
         int s = sa;
-        int k = __ldg(&A.sptr[sa]);
-        const int kb = __ldg(&A.sptr[sb]);
-        int send = __ldg(&A.sptr[s + 1]);
-        int send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-        int row = __ldg(&A.rowmap[s * 32 + lane]);
-        int row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+        int k = ld_stream(&A.sptr[sa]);
+        const int kb = ld_stream(&A.sptr[sb]);
+        int send = ld_stream(&A.sptr[s + 1]);
+        int send2 = (s + 2 <= sb) ? ld_stream(&A.sptr[s + 2]) : kb;
+        int row = ld_stream(&A.rowmap[s * 32 + lane]);
+        int row2 = (s + 1 < sb) ? ld_stream(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
 #ifndef CPK_SPMV_U
 #define CPK_SPMV_U 4
@@ -167,7 +170,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int kk = k + 32 * u + lane;
-            if (kk < kb) { cc[u] = __ldg(&A.col[kk]); vv[u] = __ldg(&A.val[kk]); } else { cc[u] = 0; vv[u] = 0.0; }
+            if (kk < kb) { cc[u] = ld_stream(&A.col[kk]); vv[u] = ld_stream(&A.val[kk]); } else { cc[u] = 0; vv[u] = 0.0; }
         }
         while (k < kb) {
             int cn[U]; double vn[U], xv[U];
@@ -175,7 +178,7 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int kk = k2 + 32 * u + lane;
-                if (kk < kb) { cn[u] = __ldg(&A.col[kk]); vn[u] = __ldg(&A.val[kk]); } else { cn[u] = 0; vn[u] = 0.0; }
+                if (kk < kb) { cn[u] = ld_stream(&A.col[kk]); vn[u] = ld_stream(&A.val[kk]); } else { cn[u] = 0; vn[u] = 0.0; }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) xv[u] = (k + 32 * u < kb) ? x[cc[u]] : 0.0;
@@ -187,8 +190,8 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
                         if (row >= 0) epi(row, acc);
                         acc = 0.0; ++s;
                         send = send2; row = row2;
-                        send2 = (s + 2 <= sb) ? __ldg(&A.sptr[s + 2]) : kb;
-                        row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+                        send2 = (s + 2 <= sb) ? ld_stream(&A.sptr[s + 2]) : kb;
+                        row2 = (s + 1 < sb) ? ld_stream(&A.rowmap[(s + 1) * 32 + lane]) : -1;
                     }
                     acc += vv[u] * xv[u];
                 }
@@ -201,17 +204,17 @@ __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const doubl
             if (row >= 0) epi(row, acc);
             acc = 0.0; ++s;
             row = row2;
-            row2 = (s + 1 < sb) ? __ldg(&A.rowmap[(s + 1) * 32 + lane]) : -1;
+            row2 = (s + 1 < sb) ? ld_stream(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         }
     }
     // long rows: one warp per row, lane-strided partial sums + butterfly
     for (int r = gwarp; r < A.nlong; r += nwarps) {
-        const int beg = __ldg(&A.lptr[r]), end = __ldg(&A.lptr[r + 1]);
+        const int beg = ld_stream(&A.lptr[r]), end = ld_stream(&A.lptr[r + 1]);
         double acc = 0.0;
-        for (int k = beg + lane; k < end; k += 32) acc += __ldg(&A.lval[k]) * x[__ldg(&A.lcol[k])];
+        for (int k = beg + lane; k < end; k += 32) acc += ld_stream(&A.lval[k]) * x[ld_stream(&A.lcol[k])];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (lane == 0) epi(__ldg(&A.lrow[r]), acc);
+        if (lane == 0) epi(ld_stream(&A.lrow[r]), acc);
     }
 }
 
@@ -297,17 +300,17 @@ struct ItemChunk { int c[4]; double v[4]; };
 
 __device__ __forceinline__ void item_load(const DevSweep &S, int t, int lane, ItemMeta &m, ItemChunk &r)
 {
-    m.beg = __ldg(&S.sptr[t]);
-    m.end = __ldg(&S.sptr[t + 1]);
+    m.beg = ld_stream(&S.sptr[t]);
+    m.end = ld_stream(&S.sptr[t + 1]);
     m.slot = item_slot(S, t, lane);
-    m.rid = __ldg(&S.rid[m.slot]);
-    m.pidx = __ldg(&S.pidx[m.slot]);
-    m.flags = __ldg(&S.flags[m.slot]);
-    m.d = __ldg(&S.d[m.slot]);
+    m.rid = ld_stream(&S.rid[m.slot]);
+    m.pidx = ld_stream(&S.pidx[m.slot]);
+    m.flags = ld_stream(&S.flags[m.slot]);
+    m.d = ld_stream(&S.d[m.slot]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int kk = m.beg + 32 * u + lane;
-        if (kk < m.end) { r.c[u] = __ldg(&S.col[kk]); r.v[u] = __ldg(&S.val[kk]); }
+        if (kk < m.end) { r.c[u] = ld_stream(&S.col[kk]); r.v[u] = ld_stream(&S.val[kk]); }
         else { r.c[u] = -1; r.v[u] = 0.0; }
     }
 }
@@ -386,7 +389,7 @@ __device__ __forceinline__ void item_process(Team &T, const DevLdl &M, const Vec
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int kk = base + 32 * u + T.lane;
-                if (kk < m.end) { c[u] = __ldg(&S.col[kk]); v[u] = __ldg(&S.val[kk]); } else { c[u] = -1; v[u] = 0.0; }
+                if (kk < m.end) { c[u] = ld_stream(&S.col[kk]); v[u] = ld_stream(&S.val[kk]); } else { c[u] = -1; v[u] = 0.0; }
             }
         }
     }
@@ -404,10 +407,10 @@ __device__ __forceinline__ void item_process(Team &T, const DevLdl &M, const Vec
         else w = TAGGED ? wait_tagged(T, &M.wbuf[m.rid], epoch) : M.wv[m.rid];
         if (!(m.flags & F_PARTNER)) acc = w / m.d;                          // opLDL2.m:86, inv(op.D)
         else {
-            const int partner = __ldg(&S.partner[m.slot]);
+            const int partner = ld_stream(&S.partner[m.slot]);
             const double wp = TAGGED ? wait_tagged(T, &M.wbuf[partner], epoch) : M.wv[partner];
-            const double e = __ldg(&S.e[m.slot]);
-            const double dp = __ldg(&S.dp[m.slot]);
+            const double e = ld_stream(&S.e[m.slot]);
+            const double dp = ld_stream(&S.dp[m.slot]);
             const double det = m.d * dp - e * e;
             acc = (dp * w - e * wp) / det;
         }
@@ -435,8 +438,8 @@ __device__ __forceinline__ void ldl_lone_rows(Team &T, const DevSweep &S, const 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * nth;
-            pi[u] = (i < nl) ? __ldg(&S.lone_pidx[i]) : -1;
-            dd[u] = (i < nl) ? __ldg(&S.lone_d[i]) : 1.0;
+            pi[u] = (i < nl) ? ld_stream(&S.lone_pidx[i]) : -1;
+            dd[u] = (i < nl) ? ld_stream(&S.lone_d[i]) : 1.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) { zz[u] = (pi[u] >= 0) ? in(pi[u]) : 0.0; oo[u] = (accumulate && pi[u] >= 0) ? out[pi[u]] : 0.0; }
@@ -458,7 +461,7 @@ __device__ __noinline__ void ldl_solve_syncfree(Team &T, const DevLdl &M, const 
     const DevSweep &S = M.sw;
     ldl_lone_rows(T, S, in, out, accumulate);
     for (int g = 0; g < S.nseg; ++g) {
-        const int sbeg = __ldg(&S.seg[3 * g]), send = __ldg(&S.seg[3 * g + 1]), blk = __ldg(&S.seg[3 * g + 2]);
+        const int sbeg = ld_stream(&S.seg[3 * g]), send = ld_stream(&S.seg[3 * g + 1]), blk = ld_stream(&S.seg[3 * g + 2]);
         const int nblk = (send - sbeg + blk - 1) / blk;
         for (int b = T.gwarp; b < nblk; b += T.nwarps) {
             int t = sbeg + b * blk;
@@ -509,15 +512,15 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
         T.cta_sync();
     }
     for (int g = 0; g < S.nlev; ++g) {
-        const int a = __ldg(&S.levptr[g]), b = __ldg(&S.levptr[g + 1]);
+        const int a = ld_stream(&S.levptr[g]), b = ld_stream(&S.levptr[g + 1]);
         if (!lone_done && a >= S.nfwd) { ldl_lone_rows(T, S, in, out, accumulate); lone_done = true; }
         const long long cnt = b - a;
         int t, tend, cs = 0;
         int *queue = &wq[g & 1];
         if (dyn) {
             if (exact) {
-                cs = __ldg(&S.ctasplit[(size_t)g * (nctas + 1) + cta]);
-                tend = __ldg(&S.ctasplit[(size_t)g * (nctas + 1) + cta + 1]);
+                cs = ld_stream(&S.ctasplit[(size_t)g * (nctas + 1) + cta]);
+                tend = ld_stream(&S.ctasplit[(size_t)g * (nctas + 1) + cta + 1]);
             } else {
                 cs = a + (int)(cnt * cta / nctas);
                 tend = a + (int)(cnt * (cta + 1) / nctas);
@@ -538,11 +541,11 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
 #pragma unroll
             for (int q = 0; q < B; ++q) {
                 if (q < nb) {
-                    beg[q] = __ldg(&S.sptr[t + q]);
-                    wid[q] = __ldg(&S.sptr[t + q + 1]) - beg[q];
+                    beg[q] = ld_stream(&S.sptr[t + q]);
+                    wid[q] = ld_stream(&S.sptr[t + q + 1]) - beg[q];
                     const int slot = item_slot(S, t + q, lane);
-                    rid[q] = __ldg(&S.rid[slot]); pidx[q] = __ldg(&S.pidx[slot]);
-                    flg[q] = __ldg(&S.flags[slot]); dd[q] = __ldg(&S.d[slot]);
+                    rid[q] = ld_stream(&S.rid[slot]); pidx[q] = ld_stream(&S.pidx[slot]);
+                    flg[q] = ld_stream(&S.flags[slot]); dd[q] = ld_stream(&S.d[slot]);
                 } else { beg[q] = 0; wid[q] = 0; rid[q] = -1; pidx[q] = 0; flg[q] = 0; dd[q] = 1.0; }
             }
             bool simple = true;
@@ -553,8 +556,8 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
 #pragma unroll
                 for (int q = 0; q < B; ++q) {
                     c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
-                    if (wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + lane]); v0[q] = __ldg(&S.val[beg[q] + lane]); }
-                    if (wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + lane]); }
+                    if (wid[q] >= 32) { c0[q] = ld_stream(&S.col[beg[q] + lane]); v0[q] = ld_stream(&S.val[beg[q] + lane]); }
+                    if (wid[q] >= 64) { c1[q] = ld_stream(&S.col[beg[q] + 32 + lane]); v1[q] = ld_stream(&S.val[beg[q] + 32 + lane]); }
                 }
                 // ---- stage B: gathers ---------------------------------------------------
                 double base[B], x0[B], x1[B];
@@ -563,7 +566,7 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
                     const bool isfwd = (flg[q] & F_FWD) != 0;
                     base[q] = 0.0; x0[q] = 0.0; x1[q] = 0.0;
                     if (rid[q] >= 0) {
-                        base[q] = (isfwd || (flg[q] & F_WDIRECT)) ? in(pidx[q]) : M.wv[rid[q]];
+                        base[q] = (isfwd || (flg[q] & F_WDIRECT)) ? in(pidx[q]) : ld_tmp(&M.wv[rid[q]]);
                         const double *depv = isfwd ? M.wv : M.yv;
                         if (c0[q] >= 0) x0[q] = (c0[q] >= Nn) ? M.wv[c0[q] - Nn] : depv[c0[q]];
                         else if (c0[q] <= -2) x0[q] = in(-c0[q] - 2);
@@ -581,10 +584,10 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
                     if (c0[q] != -1) sum -= v0[q] * x0[q];
                     if (c1[q] != -1) sum -= v1[q] * x1[q];
                     acc += sum;
-                    if (isfwd && !(flg[q] & F_FUSED)) M.wv[rid[q]] = acc;
+                    if (isfwd && !(flg[q] & F_FUSED)) st_tmp(&M.wv[rid[q]], acc);
                     else {
                         if (isfwd) acc = acc / dd[q];
-                        if (isfwd || (flg[q] & F_STORE)) M.yv[rid[q]] = acc;
+                        if (isfwd || (flg[q] & F_STORE)) st_tmp(&M.yv[rid[q]], acc);
                         if (accumulate) out[pidx[q]] = out[pidx[q]] + acc; else out[pidx[q]] = acc;
                     }
                 }
@@ -605,8 +608,8 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
                         rid0[q] = __shfl_sync(FULL, rid[q], 0); pidx0[q] = __shfl_sync(FULL, pidx[q], 0);
                         flg0[q] = __shfl_sync(FULL, flg[q], 0); d0[q] = __shfl_sync(FULL, dd[q], 0);
                         c0[q] = -1; c1[q] = -1; v0[q] = 0.0; v1[q] = 0.0;
-                        if (q < nb && wid[q] >= 32) { c0[q] = __ldg(&S.col[beg[q] + lane]); v0[q] = __ldg(&S.val[beg[q] + lane]); }
-                        if (q < nb && wid[q] >= 64) { c1[q] = __ldg(&S.col[beg[q] + 32 + lane]); v1[q] = __ldg(&S.val[beg[q] + 32 + lane]); }
+                        if (q < nb && wid[q] >= 32) { c0[q] = ld_stream(&S.col[beg[q] + lane]); v0[q] = ld_stream(&S.val[beg[q] + lane]); }
+                        if (q < nb && wid[q] >= 64) { c1[q] = ld_stream(&S.col[beg[q] + 32 + lane]); v1[q] = ld_stream(&S.val[beg[q] + 32 + lane]); }
                     }
                     double base[B], x0[B], x1[B];
 #pragma unroll
@@ -614,7 +617,7 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
                         base[q] = 0.0; x0[q] = 0.0; x1[q] = 0.0;
                         if (q < nb) {
                             const bool isfwd = (flg0[q] & F_FWD) != 0;
-                            if (lane == 0) base[q] = (isfwd || (flg0[q] & F_WDIRECT)) ? in(pidx0[q]) : M.wv[rid0[q]];
+                            if (lane == 0) base[q] = (isfwd || (flg0[q] & F_WDIRECT)) ? in(pidx0[q]) : ld_tmp(&M.wv[rid0[q]]);
                             const double *depv = isfwd ? M.wv : M.yv;
                             if (c0[q] >= 0) x0[q] = (c0[q] >= Nn) ? M.wv[c0[q] - Nn] : depv[c0[q]];
                             else if (c0[q] <= -2) x0[q] = in(-c0[q] - 2);
@@ -633,10 +636,10 @@ __device__ __noinline__ void ldl_solve_levels_impl(Team &T, const DevLdl &M, con
                             const bool isfwd = (flg0[q] & F_FWD) != 0;
                             double acc = isfwd ? base[q] : base[q] / d0[q];
                             acc += sum;
-                            if (isfwd && !(flg0[q] & F_FUSED)) M.wv[rid0[q]] = acc;
+                            if (isfwd && !(flg0[q] & F_FUSED)) st_tmp(&M.wv[rid0[q]], acc);
                             else {
                                 if (isfwd) acc = acc / d0[q];
-                                if (isfwd || (flg0[q] & F_STORE)) M.yv[rid0[q]] = acc;
+                                if (isfwd || (flg0[q] & F_STORE)) st_tmp(&M.yv[rid0[q]], acc);
                                 if (accumulate) out[pidx0[q]] = out[pidx0[q]] + acc; else out[pidx0[q]] = acc;
                             }
                         }
@@ -841,7 +844,7 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
     for (int i0 = T.tid; i0 < N; i0 += 8 * T.nthreads) {
         int pi[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? __ldg(&C.perm[i]) : -1; }
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? ld_stream(&C.perm[i]) : -1; }
         double zv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) zv[u] = (pi[u] >= 0) ? in(pi[u]) : 0.0;
@@ -885,7 +888,7 @@ __device__ __noinline__ void ldl_solve_compact(Team &T, const DevLdl &M, const V
     for (int i0 = T.tid; i0 < N; i0 += 8 * T.nthreads) {
         int pi[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? __ldg(&C.perm[i]) : -1; }
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * T.nthreads; pi[u] = (i < N) ? ld_stream(&C.perm[i]) : -1; }
         if (accumulate) {
             double ov[8];
 #pragma unroll
@@ -943,7 +946,12 @@ __device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
     }
     if (M.nitref > 0) {                                                 // :174
         double red[3];
-        resid_phase(T, M, xin, y, M.rvec, red[0], red[1], true, rider, red[2]);
+        // The residual VECTOR is only read when a refinement step follows (rare with the reference's
+        // defaults): the first pass then keeps the norms only, and the vector is produced -- same
+        // operations, same bits -- by a second pass in front of the step (CPK_LAZY_RVEC).
+        const bool lazy_r = CPK_LAZY_RVEC && !M.force_itref;
+        bool r_stored = !lazy_r;
+        resid_phase(T, M, xin, y, lazy_r ? (double *)nullptr : M.rvec, red[0], red[1], true, rider, red[2]);
         if (Rider::kActive) T.template reduce<3>(red); else { double r2[2] = {red[0], red[1]}; T.template reduce<2>(r2); red[0] = r2[0]; red[1] = r2[1]; }
         rider_valid = Rider::kActive;
         if (rider_sum) *rider_sum = red[2];
@@ -955,6 +963,14 @@ __device__ __noinline__ bool ldl2_apply(Team &T, const DevLdl &M, const VecIn xi
         int nit = 0;
         bool rknown = true;
         while (nit < M.nitref && (rNorm >= M.itref_tol * xNorm || M.force_itref)) {   // :179
+            if (!r_stored) {
+                double d0, d1, d2;
+                NoRider nr;
+                resid_phase(T, M, xin, y, M.rvec, d0, d1, false, nr, d2);
+                T.sync();
+                r_stored = true;
+                pc.mark(CPK_PH_RESID_);
+            }
             VecIn rin{M.rvec, nullptr, n, false};
             rider_valid = false;                                        // y changes: the rider's sum is stale
             ldl_solve(T, M, rin, y, true, ++epoch);                     // dy = LDL*r; y = y + dy

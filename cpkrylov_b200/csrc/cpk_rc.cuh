@@ -185,14 +185,14 @@ __device__ __forceinline__ void rc_run_long(const DevRc &R, const RcPiece pc, in
 {
     for (int r = a; r < b; ++r) {
         const int pos = pc.row_off + r;
-        const int code = __ldg(&R.rowmap[pos]);             // warp-uniform, >= 0
-        const int beg = __ldg(&R.lptr[pc.ent_off + r]), end = __ldg(&R.lptr[pc.ent_off + r + 1]);
+        const int code = ld_stream(&R.rowmap[pos]);             // warp-uniform, >= 0
+        const int beg = ld_stream(&R.lptr[pc.ent_off + r]), end = ld_stream(&R.lptr[pc.ent_off + r + 1]);
         const typename Op::Pre P = op.pre(pos, code);
         double s = 0.0;
         for (int k = beg + lane; k < end; k += 64) {
             const bool two = k + 32 < end;
-            const int c0 = __ldg(&R.lcol[k]); const double v0 = __ldg(&R.lval[k]);
-            const int c1 = __ldg(&R.lcol[two ? k + 32 : k]); const double v1 = __ldg(&R.lval[two ? k + 32 : k]);
+            const int c0 = ld_stream(&R.lcol[k]); const double v0 = ld_stream(&R.lval[k]);
+            const int c1 = ld_stream(&R.lcol[two ? k + 32 : k]); const double v1 = ld_stream(&R.lval[two ? k + 32 : k]);
             const typename Op::Raw g0 = op.gather(c0), g1 = op.gather(c1);
             s += v0 * op.value(c0, g0);
             if (two) s += v1 * op.value(c1, g1);
@@ -280,7 +280,7 @@ struct SweepOp {
             if constexpr ((MODE & 1) != 0) P.b.a = direct ? in.add[i] : 0.0;
             if constexpr ((MODE & 2) != 0) P.b.s = direct ? in.sub[i] : 0.0;
         }
-        P.dd = __ldg(&dpos[pos]);
+        P.dd = ld_stream(&dpos[pos]);
         P.o = ACC ? out[i] : 0.0;
         return P;
     }
@@ -373,7 +373,7 @@ struct ResidOp {
         const double xi = xin.value(row, P.x);
         if (wb) wb[row] = xi;                   // pending axpy of the caller lands in memory here
         const double ri = xi - s;
-        r[row] = ri;
+        if (r) r[row] = ri;
         rr += ri * ri;
         if (want_xx) xx += xi * xi;
         if (Rider::kActive) extra += rider.fin(row, xi, P.yi, P.rp);
@@ -399,7 +399,7 @@ __device__ __forceinline__ void resid_phase(Team &T, const DevLdl &M, const VecI
             const double xi = xin(row);
             if (xin.wb) xin.wb[row] = xi;       // pending axpy of the caller lands in memory here
             const double ri = xi - s;
-            r[row] = ri;
+            if (r) r[row] = ri;                 // r == nullptr: norms only (ldl2_apply stores r when a step is taken)
             rr += ri * ri;
             if (want_xx) xx += xi * xi;
             if (Rider::kActive) extra += rider.fin(row, xi, y[row], rider.pre(row));

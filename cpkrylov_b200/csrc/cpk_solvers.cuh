@@ -151,10 +151,10 @@ __device__ void run_cpcg(Ctx<Team> &c, const double *b, double *X)
         const double rn2_new = part[0];
         const double beta = rn2_new / rn2;                          // :169
         {                                                           // :161-162 and :171-172
-            const double *const src[3] = {RU, PQ, X};
-            team_map<3>(T, N, src, [&](int i, const double (&v)[3]) {
+            const double *const src[3] = {RU, PQ, X};       // RU is dead after this pass, X rests until the next one
+            team_map<3, 5u>(T, N, src, [&](int i, const double (&v)[3]) {
                 const double xi = v[2] + alpha * v[1];
-                X[i] = xi;
+                st_dead(&X[i], xi);
                 const double t = (i < n) ? v[0] : xi + v[0];
                 PQ[i] = -t + beta * v[1];
             });
