@@ -39,7 +39,7 @@ struct PhaseClock {
 #define CPK_LAZY_RVEC 1
 #endif
 #ifndef CPK_SPMV_UP
-#define CPK_SPMV_UP 8
+#define CPK_SPMV_UP 4
 #endif
 template <class Team, class Epi>
 __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, const double *x, Epi &&epi)
