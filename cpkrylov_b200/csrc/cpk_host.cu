@@ -572,10 +572,10 @@ k_matvec(DevSell A, const double *x, double *y)
 {
     if (GRID) {
         GridTeam T; T.init(nullptr, nullptr, nullptr);
-        spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
+        spmv_sell<CPK_SPMV_UP_ALONE>(T, A, x, [&](int row, double s) { y[row] = s; });
     } else {
         CtaTeam T; T.init(nullptr, nullptr, nullptr);
-        spmv_sell(T, A, x, [&](int row, double s) { y[row] = s; });
+        spmv_sell<CPK_SPMV_UP_ALONE>(T, A, x, [&](int row, double s) { y[row] = s; });
     }
 }
 

@@ -38,10 +38,16 @@ struct PhaseClock {
 #ifndef CPK_LAZY_RVEC
 #define CPK_LAZY_RVEC 1
 #endif
+// UP = packed entries per lane in flight.  Inside the solver kernels 4 (cfg 3 cpcg 3.015 -> 2.945 ms per
+// solve against 8, 3 as good, 2 slower: profiles/r2_notes.md); the product on its own (k_matvec) keeps 8
+// (cold 21 us against 23.7 us with 4).
 #ifndef CPK_SPMV_UP
 #define CPK_SPMV_UP 4
 #endif
-template <class Team, class Epi>
+#ifndef CPK_SPMV_UP_ALONE
+#define CPK_SPMV_UP_ALONE 8
+#endif
+template <int UP = CPK_SPMV_UP, class Team, class Epi>
 __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;
@@ -64,7 +70,7 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
         int row = ld_keep(&A.rowmap[s * 32 + lane]);
         int row2 = (s + 1 < sb) ? ld_keep(&A.rowmap[(s + 1) * 32 + lane]) : -1;
         double acc = 0.0;
-        constexpr int U = CPK_SPMV_UP;
+        constexpr int U = UP;
         unsigned ee[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -133,10 +139,10 @@ __device__ __forceinline__ void spmv_sell_packed(Team &T, const DevSell &A, cons
     }
 }
 
-template <class Team, class Epi>
+template <int UP = CPK_SPMV_UP, class Team, class Epi>
 __device__ __forceinline__ void spmv_sell(Team &T, const DevSell &A, const double *x, Epi &&epi)
 {
-    if (A.pk != nullptr) { spmv_sell_packed(T, A, x, epi); return; }
+    if (A.pk != nullptr) { spmv_sell_packed<UP>(T, A, x, epi); return; }
     const int lane = T.lane, gwarp = T.gwarp, nwarps = T.nwarps;      // T lives in local memory: read once
     // Each warp streams a CONTIGUOUS range of slices: the (col,val) arrays of the
     // range are one contiguous span, walked in chunks of U entries per lane with
