@@ -522,6 +522,12 @@ __device__ void run_cpsymmlq(Ctx<Team> &c, const double *b, double *X)
 // has 64 bytes per vector group in flight instead of one 8-byte load per loop trip.
 // cols / cf live in shared memory.
 // ---------------------------------------------------------------------------
+// A pass over the basis streams nc x 8N bytes (cfg 4, mem = 20: 400 MB) past an L2 that should keep the
+// matrix and the work vectors of the next phase: columns are loaded evict-first (CPK_BASIS_HINT).
+#ifndef CPK_BASIS_HINT
+#define CPK_BASIS_HINT 1
+#endif
+__device__ __forceinline__ double2 ld_basis(const double2 *p) { return CPK_BASIS_HINT ? __ldcs(p) : *p; }
 template <class Team, class Init, class Fin>
 __device__ __forceinline__ void basis_combine(const Team &T, int N, const double *B, const int *cols, const double *cf, int nc,
                                               Init &&init, Fin &&fin)
@@ -537,14 +543,14 @@ __device__ __forceinline__ void basis_combine(const Team &T, int N, const double
                 double2 a[4]; double h[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    a[q] = *reinterpret_cast<const double2 *>(B + (size_t)cols[j + q] * N + i);
+                    a[q] = ld_basis(reinterpret_cast<const double2 *>(B + (size_t)cols[j + q] * N + i));
                     h[q] = cf[j + q];
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { v0 = v0 - h[q] * a[q].x; v1 = v1 - h[q] * a[q].y; }
             }
             for (; j < nc; ++j) {
-                const double2 a = *reinterpret_cast<const double2 *>(B + (size_t)cols[j] * N + i);
+                const double2 a = ld_basis(reinterpret_cast<const double2 *>(B + (size_t)cols[j] * N + i));
                 const double h = cf[j];
                 v0 = v0 - h * a.x; v1 = v1 - h * a.y;
             }
@@ -606,7 +612,7 @@ __device__ void multi_dot(Ctx<Team> &c, const double *VQ, const int *cols, int n
                 const double2 u = *reinterpret_cast<const double2 *>(U + 2 * p);
                 double2 a[kRedMax];
 #pragma unroll
-                for (int j = 0; j < kRedMax; ++j) a[j] = *reinterpret_cast<const double2 *>(colp[j] + 2 * p);
+                for (int j = 0; j < kRedMax; ++j) a[j] = ld_basis(reinterpret_cast<const double2 *>(colp[j] + 2 * p));
 #pragma unroll
                 for (int j = 0; j < kRedMax; ++j) { acc[j] += a[j].x * u.x; acc[j] += a[j].y * u.y; }
             }
