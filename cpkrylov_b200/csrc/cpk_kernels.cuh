@@ -26,7 +26,7 @@ struct PhaseClock {
 // ---------------------------------------------------------------------------
 // SpMV, SELL-32: one lane per row, entries of a row are accumulated left to
 // right (the order a CSR/CSC CPU kernel uses).  Matrix
-// arrays are read-only for the kernel lifetime -> ld.global.nc; the vector x is
+// arrays are read-only for the kernel lifetime -> ld_stream / ld_keep (cpk_device.cuh); the vector x is
 // mutable across phases of the persistent kernel -> plain (coherent) loads.
 // Epi is called as epi(row, sum) by the lane that owns the row.
 // ---------------------------------------------------------------------------
